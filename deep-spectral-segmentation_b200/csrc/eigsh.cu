@@ -1,0 +1,473 @@
+// Smallest-K eigenpairs of the graph Laplacian pencil (D - W) v = lambda D v   (reference extract/extract.py:222-240,
+// which calls scipy.sparse.linalg.eigsh(D - W, k=K, sigma=0, which='LM', M=D): dense LU + ARPACK shift-invert).
+//
+// B200 design: no factorisation. With S = D^-1/2 W D^-1/2 the pencil's smallest eigenvalues are 1 - (largest
+// eigenvalues of S) and v = D^-1/2 u. The top eigenpair of S is known in closed form (u0 = D^1/2 1 / sqrt(sum D),
+// mu0 = 1) and is deflated analytically; the next K-1 come from Lanczos with full re-orthogonalisation (two
+// classical Gram-Schmidt passes) -- ~16-50 symmetric mat-vecs per image instead of an N^3 LU.
+//
+// One persistent CTA per image: the whole iteration (mat-vec, re-orthogonalisation, Ritz extraction, convergence
+// test) runs inside one kernel with block-level barriers only; images are independent, so a batch fills the GPU
+// with one CTA (or more) per SM and nothing ever synchronises across CTAs. W (N^2 fp32, 3.2 MB at N=900) is
+// streamed once per mat-vec (L2-resident for typical batches); the Lanczos basis lives in a per-CTA global
+// scratch (L2), the working vectors in shared memory. Ritz values of the tridiagonal matrix come from a 32-way
+// Sturm multisection in fp64 (one warp per eigenvalue), Ritz vectors from a twisted factorisation.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace dss {
+
+constexpr int EIG_THREADS = 512;
+constexpr int EIG_WARPS = EIG_THREADS / 32;
+constexpr int EIG_MAX_K = 64;
+
+struct EigParams {
+  const float* W;     // [B, N, ldw]
+  float* evals;       // [B, K]
+  float* evecs;       // [B, K, N]
+  int* info;          // [B, 4]
+  float* resid;       // [B, K] or null
+  float* basis;       // per-CTA scratch: [(mmax+1), Npad]
+  double* tri;        // per-CTA scratch: [2, Kw, mmax]   (Ritz vectors of T, temp)
+  int B, N, ldw, Npad, K, mmax, lapnorm;
+  float tol;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {
+  v = warp_sum(v);
+  __syncthreads();  // protect red from the previous use
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < EIG_WARPS; ++i) s += red[i];
+  return s;
+}
+
+__device__ __forceinline__ float hash_uniform(uint32_t i, uint32_t seed) {
+  uint32_t x = i * 2654435761u ^ (seed * 0x9E3779B9u + 0x85EBCA6Bu);
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return (float)(x >> 8) * (2.0f / 16777216.0f) - 1.0f;
+}
+
+// dot of a global (or shared) vector with the shared vector w, whole warp, float4 path when Npad-aligned
+__device__ __forceinline__ float warp_dot(const float* __restrict__ a, const float* __restrict__ w, int N, int lane) {
+  float s0 = 0.f, s1 = 0.f;
+  const int n4 = N >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  for (int i = lane; i < n4; i += 32) {
+    const float4 x = a4[i], y = w4[i];
+    s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1);
+    s0 = fmaf(x.z, y.z, s0); s1 = fmaf(x.w, y.w, s1);
+  }
+  for (int i = (n4 << 2) + lane; i < N; i += 32) s0 = fmaf(a[i], w[i], s0);
+  return warp_sum(s0 + s1);
+}
+
+// number of eigenvalues of the n x n tridiagonal (alpha, beta) that are < x
+__device__ __forceinline__ int sturm_count(const double* alpha, const double* beta2, int n, double x) {
+  int cnt = 0;
+  double q = alpha[0] - x;
+  if (q == 0.0) q = -1e-300;
+  cnt += q < 0.0;
+  for (int i = 1; i < n; ++i) {
+    q = (alpha[i] - x) - beta2[i - 1] / q;
+    if (q == 0.0) q = -1e-300;
+    cnt += q < 0.0;
+  }
+  return cnt;
+}
+
+__host__ __device__ inline size_t eig_double_bytes(int mmax) {
+  size_t nd = (size_t)3 * mmax + 2 * EIG_MAX_K + EIG_WARPS;
+  nd = (nd + 1) & ~(size_t)1;
+  return nd * sizeof(double);
+}
+
+__global__ void __launch_bounds__(EIG_THREADS, 2)
+lanczos_laplacian_kernel(EigParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int N = p.N, Npad = p.Npad, mmax = p.mmax, K = p.K, Kw = p.K - 1, ldw = p.ldw;
+  // shared layout
+  double* alpha = reinterpret_cast<double*>(smem_raw);      // [mmax]
+  double* beta = alpha + mmax;                               // [mmax]   beta[j] = ||w_j|| (couples j, j+1)
+  double* beta2 = beta + mmax;                               // [mmax]
+  double* theta = beta2 + mmax;                              // [EIG_MAX_K]
+  double* red = theta + EIG_MAX_K;                           // [EIG_WARPS]
+  double* resid_s = red + EIG_WARPS;                         // [EIG_MAX_K]
+  // float arrays start 16-byte aligned (float4 access): the double block is padded to an even count
+  float* xs = reinterpret_cast<float*>(smem_raw + eig_double_bytes(mmax));  // [Npad] scaled mat-vec input
+  float* wv = xs + Npad;                                     // [Npad] working vector
+  float* vcur = wv + Npad;                                   // [Npad] current Lanczos vector
+  float* dsc = vcur + Npad;                                  // [Npad] D^-1/2 (lapnorm) or D (unnormalised)
+  float* u0 = dsc + Npad;                                    // [Npad] deflated null vector (unit 2-norm)
+  float* coef = u0 + Npad;                                   // [mmax + 2]
+  __shared__ int s_flag;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* basis = p.basis + (size_t)blockIdx.x * (size_t)(mmax + 1) * Npad;
+  double* triS = p.tri + (size_t)blockIdx.x * 2 * (size_t)(Kw > 0 ? Kw : 1) * mmax;  // [Kw][mmax] Ritz vectors of T
+  double* triB = triS + (size_t)(Kw > 0 ? Kw : 1) * mmax;                             // [Kw][mmax] temp
+
+  for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+    const float* W = p.W + (size_t)img * N * ldw;
+    __syncthreads();
+    // ---- degree D = W 1  (row_sum, extract_utils.py:217), clamp < 1e-12 -> 1 (:218)
+    for (int r = warp; r < N; r += EIG_WARPS) {
+      const float4* row = reinterpret_cast<const float4*>(W + (size_t)r * ldw);
+      float s0 = 0.f, s1 = 0.f;
+      for (int i = lane; i < (Npad >> 2); i += 32) {  // pad columns [N, Npad) are zero
+        const float4 v = __ldg(row + i);
+        s0 += v.x + v.y; s1 += v.z + v.w;
+      }
+      const float s = warp_sum(s0 + s1);
+      if (lane == 0) wv[r] = s;
+    }
+    __syncthreads();
+    double part = 0.0;
+    int clamped = 0;
+    for (int i = tid; i < Npad; i += EIG_THREADS) {
+      float dg = 0.f;
+      if (i < N) {
+        dg = wv[i];
+        if (dg < 1e-12f) { dg = 1.0f; clamped = 1; }
+        part += (double)dg;
+      }
+      wv[i] = dg;
+    }
+    const double sumD = block_sum(part, red, tid);
+    for (int i = tid; i < Npad; i += EIG_THREADS) {
+      const float dg = wv[i];
+      if (i < N) {
+        if (p.lapnorm) {
+          dsc[i] = (float)(1.0 / sqrt((double)dg));
+          u0[i] = (float)(sqrt((double)dg) / sqrt(sumD));
+        } else {
+          dsc[i] = dg;
+          u0[i] = (float)(1.0 / sqrt((double)N));
+        }
+      } else {
+        dsc[i] = 0.f; u0[i] = 0.f;
+      }
+      xs[i] = 0.f; vcur[i] = 0.f;
+    }
+    __syncthreads();
+    (void)clamped;
+
+    int n = 0;          // Lanczos steps done
+    int converged = (Kw <= 0);
+    if (Kw > 0) {
+      // ---- start vector: deterministic pseudo-random, orthogonal to u0
+      for (int i = tid; i < Npad; i += EIG_THREADS) wv[i] = (i < N) ? hash_uniform((uint32_t)i, 0x1234567u) : 0.f;
+      __syncthreads();
+      for (int pass = 0; pass < 2; ++pass) {
+        double d = 0.0;
+        for (int i = tid; i < N; i += EIG_THREADS) d += (double)wv[i] * (double)u0[i];
+        const float c = (float)block_sum(d, red, tid);
+        for (int i = tid; i < N; i += EIG_THREADS) wv[i] = fmaf(-c, u0[i], wv[i]);
+        __syncthreads();
+      }
+      {
+        double d = 0.0;
+        for (int i = tid; i < N; i += EIG_THREADS) d += (double)wv[i] * (double)wv[i];
+        const float inv = (float)(1.0 / sqrt(block_sum(d, red, tid)));
+        for (int i = tid; i < Npad; i += EIG_THREADS) {
+          const float v = (i < N) ? wv[i] * inv : 0.f;
+          vcur[i] = v;
+          basis[i] = v;
+        }
+      }
+      __syncthreads();
+
+      double anorm = 1.0;
+      for (int j = 0; j < mmax; ++j) {
+        // ---- mat-vec  w = S v  (lapnorm)   or   w = (W - D) v  (unnormalised: top of -(D-W))
+        for (int i = tid; i < Npad; i += EIG_THREADS) xs[i] = p.lapnorm ? dsc[i] * vcur[i] : vcur[i];
+        __syncthreads();
+        for (int r = warp * 2; r < N; r += EIG_WARPS * 2) {
+          const bool two = (r + 1) < N;
+          const float4* row0 = reinterpret_cast<const float4*>(W + (size_t)r * ldw);
+          const float4* row1 = reinterpret_cast<const float4*>(W + (size_t)(two ? r + 1 : r) * ldw);
+          const float4* x4 = reinterpret_cast<const float4*>(xs);
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+          for (int i = lane; i < (Npad >> 2); i += 32) {
+            const float4 x = x4[i];
+            const float4 u = __ldg(row0 + i);
+            const float4 v = __ldg(row1 + i);
+            a0 = fmaf(u.x, x.x, a0); a1 = fmaf(u.y, x.y, a1); a0 = fmaf(u.z, x.z, a0); a1 = fmaf(u.w, x.w, a1);
+            b0 = fmaf(v.x, x.x, b0); b1 = fmaf(v.y, x.y, b1); b0 = fmaf(v.z, x.z, b0); b1 = fmaf(v.w, x.w, b1);
+          }
+          const float sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
+          if (lane == 0) {
+            wv[r] = p.lapnorm ? dsc[r] * sa : sa - dsc[r] * xs[r];
+            if (two) wv[r + 1] = p.lapnorm ? dsc[r + 1] * sb : sb - dsc[r + 1] * xs[r + 1];
+          }
+        }
+        __syncthreads();
+        // ---- full re-orthogonalisation (CGS2) against u0, v_0..v_j ; alpha_j = sum of the v_j coefficients
+        double aj = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int i = warp; i < j + 2; i += EIG_WARPS) {
+            const float* a = (i == 0) ? u0 : ((i - 1 == j) ? vcur : basis + (size_t)(i - 1) * Npad);
+            const float c = warp_dot(a, wv, N, lane);
+            if (lane == 0) coef[i] = c;
+          }
+          __syncthreads();
+          aj += (double)coef[j + 1];
+          for (int i = tid; i < N; i += EIG_THREADS) {
+            float acc = coef[0] * u0[i];
+            for (int t = 0; t < j; ++t) acc = fmaf(coef[t + 1], basis[(size_t)t * Npad + i], acc);
+            acc = fmaf(coef[j + 1], vcur[i], acc);
+            wv[i] -= acc;
+          }
+          __syncthreads();
+        }
+        double d = 0.0;
+        for (int i = tid; i < N; i += EIG_THREADS) d += (double)wv[i] * (double)wv[i];
+        const double bj = sqrt(block_sum(d, red, tid));
+        if (tid == 0) {
+          alpha[j] = aj;
+          beta[j] = bj;
+          beta2[j] = bj * bj;
+        }
+        n = j + 1;
+        anorm = fmax(anorm, fabs(aj) + bj);
+        const bool breakdown = !(bj > 1e-7 * anorm);   // invariant subspace: all Ritz pairs are exact
+        if (!breakdown) {
+          const float inv = (float)(1.0 / bj);
+          float* vn = basis + (size_t)(j + 1) * Npad;
+          for (int i = tid; i < Npad; i += EIG_THREADS) {
+            const float v = (i < N) ? wv[i] * inv : 0.f;
+            vcur[i] = v;
+            vn[i] = v;
+          }
+        }
+        __syncthreads();
+
+        // ---- convergence test on the K-1 largest Ritz pairs of T_n
+        const int n0 = max(Kw + 4, 12);
+        const int every = (n <= 64) ? 4 : 8;
+        const bool check = breakdown || n == mmax || n >= N - 1 || (n >= n0 && ((n - n0) % every) == 0);
+        const int kk = min(Kw, n);  // Ritz pairs that exist
+        if (check) {
+          // Gershgorin bounds (every warp computes them redundantly: n <= mmax small)
+          double gl = 1e300, gh = -1e300;
+          for (int i = lane; i < n; i += 32) {
+            const double off = (i > 0 ? beta[i - 1] : 0.0) + (i < n - 1 ? beta[i] : 0.0);
+            gl = fmin(gl, alpha[i] - off);
+            gh = fmax(gh, alpha[i] + off);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+            gh = fmax(gh, __shfl_xor_sync(0xffffffffu, gh, o));
+          }
+          const double span = fmax(gh - gl, 1e-30);
+          gl -= 1e-3 * span; gh += 1e-3 * span;
+          for (int k = warp; k < kk; k += EIG_WARPS) {
+            // k-th largest eigenvalue = ascending index t = n-1-k ; lambda_t >= x  <=>  count(x) <= t
+            const int t = n - 1 - k;
+            double lo = gl, hi = gh;
+            for (int round = 0; round < 11; ++round) {
+              const double step = (hi - lo) / 33.0;
+              const double x = lo + step * (double)(lane + 1);
+              const int c = sturm_count(alpha, beta2, n, x);
+              const unsigned mask = __ballot_sync(0xffffffffu, c <= t);
+              const int np = __popc(mask);  // predicate is monotone: true for a prefix of lanes
+              const double nlo = (np > 0) ? lo + step * (double)np : lo;
+              const double nhi = (np < 32) ? lo + step * (double)(np + 1) : hi;
+              lo = nlo; hi = nhi;
+            }
+            const double th = 0.5 * (lo + hi);
+            // Ritz vector of T by twisted factorisation of T - th I (lane 0, sequential recurrences)
+            double* zs = triS + (size_t)k * mmax;
+            double* tb = triB + (size_t)k * mmax;
+            if (lane == 0) {
+              if (n == 1) {
+                zs[0] = 1.0;
+              } else {
+                double dp = alpha[0] - th;
+                for (int i = 0; i < n - 1; ++i) {
+                  if (dp == 0.0) dp = 1e-300;
+                  zs[i] = dp;
+                  dp = (alpha[i + 1] - th) - beta2[i] / dp;
+                }
+                if (dp == 0.0) dp = 1e-300;
+                zs[n - 1] = dp;
+                double dm = alpha[n - 1] - th;
+                double gmin = fabs(zs[n - 1] + dm - (alpha[n - 1] - th));
+                int r = n - 1;
+                if (dm == 0.0) dm = 1e-300;
+                tb[n - 1] = dm;
+                for (int i = n - 2; i >= 0; --i) {
+                  dm = (alpha[i] - th) - beta2[i] / dm;
+                  if (dm == 0.0) dm = 1e-300;
+                  tb[i] = dm;
+                  const double g = fabs(zs[i] + dm - (alpha[i] - th));
+                  if (g < gmin) { gmin = g; r = i; }
+                }
+                // z_r = 1 ; upward z_i = -beta_i z_{i+1} / d+_i ; downward z_{i+1} = -beta_i z_i / d-_{i+1}
+                double z = 1.0;
+                const double dpr = zs[r];
+                (void)dpr;
+                zs[r] = 1.0;
+                // upward needs d+_i for i < r which are still stored in zs[i]
+                for (int i = r - 1; i >= 0; --i) {
+                  z = -beta[i] * z / zs[i];
+                  zs[i] = z;
+                }
+                z = 1.0;
+                for (int i = r; i < n - 1; ++i) {
+                  z = -beta[i] * z / tb[i + 1];
+                  zs[i + 1] = z;
+                }
+              }
+            }
+            __syncwarp();
+            double nn = 0.0;
+            for (int i = lane; i < n; i += 32) nn += zs[i] * zs[i];
+            nn = warp_sum(nn);
+            const double inv = 1.0 / sqrt(nn);
+            for (int i = lane; i < n; i += 32) zs[i] *= inv;
+            __syncwarp();
+            if (lane == 0) {
+              theta[k] = th;
+              resid_s[k] = fabs(beta[n - 1] * zs[n - 1]);
+            }
+          }
+          __syncthreads();
+          if (tid == 0) {
+            int ok = 1;
+            for (int k = 0; k < kk; ++k) ok &= (resid_s[k] <= (double)p.tol * anorm);
+            ok &= (kk == Kw);
+            s_flag = ok;
+          }
+          __syncthreads();
+          converged = s_flag;
+          if (converged || breakdown) break;
+        }
+      }
+    }
+
+    // ---- outputs: ascending eigenvalues, D-orthonormal (lapnorm) / unit (unnormalised) vectors, sign rule
+    float* ev = p.evals + (size_t)img * K;
+    float* evec = p.evecs + (size_t)img * K * N;
+    {
+      const float c0 = p.lapnorm ? (float)(1.0 / sqrt(sumD)) : (float)(1.0 / sqrt((double)N));
+      for (int i = tid; i < N; i += EIG_THREADS) evec[i] = c0;
+      if (tid == 0) {
+        ev[0] = 0.f;
+        if (p.resid) p.resid[(size_t)img * K] = 0.f;
+        p.info[img * 4 + 0] = n;
+        p.info[img * 4 + 1] = converged ? 1 : 0;
+        p.info[img * 4 + 2] = 0;
+        p.info[img * 4 + 3] = 0;
+      }
+    }
+    const int have = min(Kw, n);  // Ritz pairs available
+    for (int k = 0; k < Kw; ++k) {
+      float* out = evec + (size_t)(k + 1) * N;
+      if (k >= have) {  // degenerate request (K-1 > steps possible): fill with NaN
+        for (int i = tid; i < N; i += EIG_THREADS) out[i] = __int_as_float(0x7fc00000);
+        if (tid == 0) ev[k + 1] = __int_as_float(0x7fc00000);
+        continue;
+      }
+      const double* zs = triS + (size_t)k * mmax;
+      double d = 0.0;
+      for (int i = tid; i < N; i += EIG_THREADS) {
+        float acc = 0.f;
+        for (int t = 0; t < n; ++t) acc = fmaf((float)zs[t], basis[(size_t)t * Npad + i], acc);
+        wv[i] = acc;
+        d += (double)acc * (double)acc;
+      }
+      const float inv = (float)(1.0 / sqrt(block_sum(d, red, tid)));
+      int pos = 0;
+      for (int i = tid; i < N; i += EIG_THREADS) {
+        const float v = p.lapnorm ? wv[i] * inv * dsc[i] : wv[i] * inv;
+        wv[i] = v;
+        pos += v > 0.f;
+      }
+      const int npos = (int)(block_sum((double)pos, red, tid) + 0.5);
+      // sign rule (extract.py:237-240): flip iff 0.5 < mean(v > 0) < 1.0
+      const float sgn = (2 * npos > N && npos < N) ? -1.f : 1.f;
+      for (int i = tid; i < N; i += EIG_THREADS) out[i] = sgn * wv[i];
+      if (tid == 0) {
+        ev[k + 1] = p.lapnorm ? (float)(1.0 - theta[k]) : (float)(-theta[k]);
+        if (p.resid) p.resid[(size_t)img * K + k + 1] = (float)resid_s[k];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+static size_t eig_smem_bytes(int Npad, int mmax) {
+  return eig_double_bytes(mmax) + (size_t)5 * Npad * sizeof(float) + (size_t)(mmax + 2) * sizeof(float) + 16;
+}
+
+static int eig_resolve(int N, int K, int max_steps) {
+  int mmax = max_steps > 0 ? max_steps : 320;
+  if (mmax > N - 1) mmax = N - 1;
+  if (mmax < K) mmax = K;
+  if (mmax < 1) mmax = 1;
+  return mmax;
+}
+
+static int eig_grid(int B, int Npad, int mmax) {
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const size_t smem = eig_smem_bytes(Npad, mmax);
+  int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);  // 512 threads, <=64 regs => at most 2 CTAs / SM
+  int g = sms * per_sm;
+  return B < g ? B : g;
+}
+
+}  // namespace dss
+
+using namespace dss;
+
+extern "C" size_t dss_eigsh_workspace_bytes(int B, int N, int K, int max_steps) {
+  if (B <= 0 || N <= 0 || K <= 0) return 0;
+  const int Npad = (N + 3) & ~3;
+  const int mmax = eig_resolve(N, K, max_steps);
+  const int grid = eig_grid(B, Npad, mmax);
+  const size_t basis = align_up((size_t)grid * (mmax + 1) * Npad * sizeof(float), 256);
+  const size_t tri = align_up((size_t)grid * 2 * (K > 1 ? K - 1 : 1) * mmax * sizeof(double), 256);
+  return basis + tri;
+}
+
+extern "C" int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int K, int lapnorm, float tol,
+                                   int max_steps, float* evals, float* evecs, int* info, float* resid, void* ws,
+                                   size_t ws_bytes, dss_stream_t stream) {
+  DSS_REQUIRE(Wmat && evals && evecs && info && ws, "eigsh: null pointer");
+  DSS_REQUIRE(B > 0 && N > 1, "eigsh: empty problem B=%d N=%d", B, N);
+  DSS_REQUIRE(K >= 1 && K <= EIG_MAX_K && K < N, "eigsh: need 1 <= K <= %d and K < N (K=%d N=%d)", EIG_MAX_K, K, N);
+  DSS_REQUIRE(ldw >= N && ldw % 4 == 0, "eigsh: ldw must be >= N and a multiple of 4 (N=%d ldw=%d)", N, ldw);
+  DSS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0 && (reinterpret_cast<uintptr_t>(Wmat) & 15) == 0,
+              "eigsh: workspace must be 256-byte aligned and W 16-byte aligned");
+  const size_t need = dss_eigsh_workspace_bytes(B, N, K, max_steps);
+  if (ws_bytes < need) {
+    set_error("eigsh: workspace too small (%zu < %zu)", ws_bytes, need);
+    return DSS_ERR_WORKSPACE;
+  }
+  EigParams p;
+  p.W = Wmat; p.evals = evals; p.evecs = evecs; p.info = info; p.resid = resid;
+  p.B = B; p.N = N; p.ldw = ldw; p.Npad = (N + 3) & ~3; p.K = K; p.lapnorm = lapnorm ? 1 : 0;
+  p.mmax = eig_resolve(N, K, max_steps);
+  p.tol = tol > 0.f ? tol : 1e-6f;
+  const int grid = eig_grid(B, p.Npad, p.mmax);
+  p.basis = reinterpret_cast<float*>(ws);
+  p.tri = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(ws) +
+                                    align_up((size_t)grid * (p.mmax + 1) * p.Npad * sizeof(float), 256));
+  const size_t smem = eig_smem_bytes(p.Npad, p.mmax);
+  if (smem > 227 * 1024) {
+    set_error("eigsh: N=%d with max_steps=%d needs %zu B of shared memory (> 227 KB)", N, p.mmax, smem);
+    return DSS_ERR_UNSUPPORTED;
+  }
+  DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lanczos_laplacian_kernel<<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  DSS_CHECK_CUDA(cudaGetLastError());
+  return DSS_OK;
+}

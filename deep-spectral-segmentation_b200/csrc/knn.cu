@@ -1,0 +1,117 @@
+// Colour KNN affinity (reference extract/extract_utils.py:151-188, which calls pymatting.util.kdtree.knn).
+//
+// For every low-resolution pixel i the reference finds its k nearest pixels (itself included) in the 5-D space
+// (r, g, b, w*x, w*y), twice: (k=20, w=2.0) and (k=10, w=0.1), and builds csr_matrix((1, (ij, ji))) with
+// ij = [i.., j..], ji = [j.., i..]; duplicates are summed, so each directed neighbour pair (i -> j) adds 1 to
+// W[i,j] and 1 to W[j,i]. This kernel does an exact brute-force KNN (N <= 6400 points: a KD-tree buys nothing on a
+// GPU) and accumulates the same dense matrix as uint8 counts (max value 4).
+//
+// One warp per query point; the image's points sit in shared memory (SoA). Neighbours are extracted in
+// increasing (squared distance, index) order by k successive warp-wide arg-min sweeps; squared distances are
+// accumulated in fp32 dimension by dimension without FMA contraction so that ties/orderings are reproducible
+// bit-for-bit by the CPU oracle (oracle/eigs_ref.py:knn_exact).
+#include "common.cuh"
+
+namespace dss {
+
+constexpr int KNN_WARPS = 8;
+
+__device__ __forceinline__ float sqdist5(const float* __restrict__ pts, int N, int j, const float (&q)[5]) {
+  float d2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const float diff = __fsub_rn(q[c], pts[c * N + j]);
+    d2 = __fadd_rn(d2, __fmul_rn(diff, diff));
+  }
+  return d2;
+}
+
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_counts_kernel(const float* __restrict__ rgb, uint32_t* __restrict__ counts_words, int N, int Hl, int Wl, int k,
+                  double weight) {
+  extern __shared__ float pts[];  // [5][N]
+  const int b = blockIdx.y;
+  const float* src = rgb + (size_t)b * N * 3;
+  const double sx = Wl > 1 ? 1.0 / (double)(Wl - 1) : 0.0;  // np.linspace(0, 1, w) step
+  const double sy = Hl > 1 ? 1.0 / (double)(Hl - 1) : 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int col = i % Wl, row = i / Wl;
+    pts[0 * N + i] = src[i * 3 + 0];
+    pts[1 * N + i] = src[i * 3 + 1];
+    pts[2 * N + i] = src[i * 3 + 2];
+    const double x = (col == Wl - 1 && Wl > 1) ? 1.0 : (double)col * sx;
+    const double y = (row == Hl - 1 && Hl > 1) ? 1.0 : (double)row * sy;
+    pts[3 * N + i] = (float)(weight * x);
+    pts[4 * N + i] = (float)(weight * y);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * KNN_WARPS + warp;
+  if (qi >= N) return;
+  float q[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) q[c] = pts[c * N + qi];
+  uint32_t* cw = counts_words + ((size_t)b * N * N) / 4;  // host guarantees (B*N*N) % 4 == 0 per image via padding check
+  const size_t img_off_bytes = ((size_t)b * N * N) & 3;    // == 0 (checked on host)
+  (void)img_off_bytes;
+  // last selected key (d2, idx); start below everything
+  float last_d = -1.f;
+  int last_j = -1;
+  for (int r = 0; r < k; ++r) {
+    float best_d = INFINITY;
+    int best_j = 0x7fffffff;
+    for (int j = lane; j < N; j += 32) {
+      const float d2 = sqdist5(pts, N, j, q);
+      const bool after = (d2 > last_d) || (d2 == last_d && j > last_j);
+      const bool better = (d2 < best_d) || (d2 == best_d && j < best_j);
+      if (after && better) { best_d = d2; best_j = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, best_d, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+      if (od < best_d || (od == best_d && oj < best_j)) { best_d = od; best_j = oj; }
+    }
+    last_d = best_d;
+    last_j = best_j;
+    if (lane == 0 && best_j < N) {
+      const size_t e0 = (size_t)qi * N + best_j, e1 = (size_t)best_j * N + qi;
+      atomicAdd(cw + (e0 >> 2), 1u << (8 * (e0 & 3)));
+      atomicAdd(cw + (e1 >> 2), 1u << (8 * (e1 & 3)));
+    }
+  }
+}
+
+}  // namespace dss
+
+using namespace dss;
+
+extern "C" size_t dss_knn_workspace_bytes(int B, int N) {
+  (void)B; (void)N;
+  return 256;  // no scratch needed; kept for ABI symmetry
+}
+
+extern "C" int dss_knn_color_counts(const float* rgb, int B, int Hl, int Wl, uint8_t* counts, void* ws,
+                                    size_t ws_bytes, dss_stream_t stream) {
+  (void)ws; (void)ws_bytes;
+  DSS_REQUIRE(rgb && counts, "knn: null pointer");
+  DSS_REQUIRE(B > 0 && Hl > 0 && Wl > 0, "knn: empty problem");
+  const int N = Hl * Wl;
+  DSS_REQUIRE(N >= 20, "knn: need at least 20 points (k=20 neighbours), got %d", N);
+  DSS_REQUIRE(((size_t)N * N) % 4 == 0 && (reinterpret_cast<uintptr_t>(counts) & 3) == 0,
+              "knn: N*N must be a multiple of 4 and counts 4-byte aligned (N=%d)", N);
+  const size_t smem = (size_t)5 * N * sizeof(float);
+  DSS_REQUIRE(smem <= 200 * 1024, "knn: N=%d points do not fit in shared memory", N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DSS_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * N * N, st));
+  DSS_CHECK_CUDA(cudaFuncSetAttribute(knn_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(N, KNN_WARPS), B);
+  const int ks[2] = {20, 10};
+  const double ws_[2] = {2.0, 0.1};
+  for (int pass = 0; pass < 2; ++pass) {
+    knn_counts_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(rgb, reinterpret_cast<uint32_t*>(counts), N, Hl, Wl, ks[pass],
+                                                          ws_[pass]);
+    DSS_CHECK_CUDA(cudaGetLastError());
+  }
+  return DSS_OK;
+}

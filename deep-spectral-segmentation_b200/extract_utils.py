@@ -1,0 +1,83 @@
+"""Host utilities of the hot path: same names and behaviour as the reference's extract/extract_utils.py
+(ImagesDataset :17-37, get_model :40-50, get_image_sizes :73-79, make_output_dir :98-104, parallel_process :138-148)."""
+from __future__ import annotations
+
+import sys
+import time
+from pathlib import Path
+from typing import Callable, Iterable, Optional
+
+import numpy as np
+import torch
+
+from .vit import get_model  # noqa: F401  (re-exported under the reference's name)
+
+
+def read_image_rgb(path) -> np.ndarray:
+    """cv2.imread + BGR->RGB (extract_utils.py:30-31) -> uint8 (H, W, 3). PIL is the fallback decoder."""
+    try:
+        import cv2
+        img = cv2.imread(str(path))
+        if img is None:
+            raise IOError(f"cannot decode {path}")
+        return cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    except ImportError:
+        from PIL import Image
+        return np.asarray(Image.open(str(path)).convert("RGB"))
+
+
+class ImagesDataset:
+    """De-duplicated, sorted list of image files; items are (uint8 RGB HWC tensor, path, index).
+
+    The reference's transform (ToTensor + Normalize) is fused into the device patch-embedding kernel, so items stay
+    uint8: 4x fewer bytes over PCIe than the reference's fp32 CHW tensors."""
+
+    def __init__(self, filenames, images_root: Optional[str] = None, transform: Optional[Callable] = None,
+                 prepare_filenames: bool = True) -> None:
+        self.root = None if images_root is None else Path(images_root)
+        self.filenames = sorted(list(set(filenames))) if prepare_filenames else list(filenames)
+        self.transform = transform
+
+    def __getitem__(self, index: int):
+        path = self.filenames[index]
+        full_path = Path(path) if self.root is None else self.root / path
+        assert full_path.is_file(), f"Not a file: {full_path}"
+        image = torch.from_numpy(np.ascontiguousarray(read_image_rgb(full_path)))
+        if self.transform is not None:
+            image = self.transform(image)
+        return image, path, index
+
+    def __len__(self) -> int:
+        return len(self.filenames)
+
+
+def get_image_sizes(data_dict: dict, downsample_factor: Optional[int] = None):
+    P = data_dict["patch_size"] if downsample_factor is None else downsample_factor
+    B, C, H, W = data_dict["shape"]
+    assert B == 1, "assumption violated :("
+    H_patch, W_patch = H // P, W // P
+    H_pad, W_pad = H_patch * P, W_patch * P
+    return (B, C, H, W, P, H_patch, W_patch, H_pad, W_pad)
+
+
+def make_output_dir(output_dir, check_if_empty=True, assume_yes: Optional[bool] = None):
+    """Creates the directory; like the reference it asks before writing into a non-empty one. When stdin is not a
+    terminal (batch jobs, tests) or assume_yes is set, it continues without blocking (skip-if-exists makes that safe)."""
+    output_dir = Path(output_dir)
+    output_dir.mkdir(exist_ok=True, parents=True)
+    if check_if_empty and (len(list(output_dir.iterdir())) > 0):
+        print(f"Output dir: {str(output_dir)}")
+        if assume_yes or (assume_yes is None and not sys.stdin.isatty()):
+            print("Output dir already contains files. Continuing (existing outputs are skipped).")
+            return
+        if input("Output dir already contains files. Continue? (y/n) >> ") != "y":
+            sys.exit()
+
+
+def parallel_process(inputs: Iterable, fn: Callable, multiprocessing: int = 0):
+    """Serial driver with the reference's timing print. ``multiprocessing`` is accepted for CLI compatibility; the
+    GPU path batches images inside each kernel instead of forking CPU workers."""
+    start = time.time()
+    for inp in inputs:
+        fn(inp)
+    print(f"Finished in {time.time() - start:.1f}s")

@@ -1,0 +1,108 @@
+"""Host side of the affinity / colour-KNN / eigensolver stage (mirror of the arithmetic in
+extract/extract.py:148,191-240 and extract/extract_utils.py:151-220). Device work: csrc/affinity.cu, knn.cu, eigsh.cu."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+class _Scratch:
+    """Grow-only device scratch buffers keyed by purpose (caller-owned workspaces of the C ABI)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, key, nbytes, device):
+        b = self.bufs.get((key, device))
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self.bufs[(key, device)] = b
+        return b
+
+
+_scratch = _Scratch()
+
+
+def pitch(N: int) -> int:
+    """Row pitch of the affinity matrix: rows padded to a multiple of 4 floats (16 B) for vector loads."""
+    return (N + 3) // 4 * 4
+
+
+@torch.no_grad()
+def knn_color_counts(rgb_lr: torch.Tensor, Hl: int, Wl: int) -> torch.Tensor:
+    """rgb_lr [B, Hl*Wl, 3] fp32 CUDA in [0,1] -> dense KNN colour affinity counts [B, N, N] uint8."""
+    _lib.require_cuda(rgb_lr, "rgb_lr")
+    lib = _lib.load()
+    rgb = rgb_lr.to(torch.float32).contiguous()
+    B, N, _ = rgb.shape
+    assert N == Hl * Wl
+    with torch.cuda.device(rgb.device):
+        counts = torch.empty(B, N, N, dtype=torch.uint8, device=rgb.device)
+        _lib.check(lib.dss_knn_color_counts(rgb.data_ptr(), B, Hl, Wl, counts.data_ptr(), None, 0,
+                                            _lib.stream_ptr(rgb.device)), "dss_knn_color_counts")
+    return counts
+
+
+@torch.no_grad()
+def affinity(feats: torch.Tensor, normalize=True, threshold_at_zero=True, color_counts: Optional[torch.Tensor] = None,
+             color_lambda: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """feats [B, N, d] fp32 CUDA -> W [B, N, pitch(N)] fp32 (columns >= N are zero)."""
+    _lib.require_cuda(feats, "feats")
+    lib = _lib.load()
+    f = feats.to(torch.float32).contiguous()
+    B, N, d = f.shape
+    ldw = pitch(N)
+    dev = f.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty(B, N, ldw, dtype=torch.float32, device=dev)
+        need = int(lib.dss_affinity_workspace_bytes(B, N, d))
+        ws = _scratch.get("aff", need, dev)
+        flags = (_lib.AFF_NORMALIZE if normalize else 0) | (_lib.AFF_THRESHOLD_AT_ZERO if threshold_at_zero else 0)
+        cc = None
+        if color_counts is not None and color_lambda > 0:
+            cc = color_counts.contiguous()
+            assert cc.dtype == torch.uint8 and tuple(cc.shape) == (B, N, N)
+        _lib.check(lib.dss_affinity(f.data_ptr(), B, N, d, flags, _lib.ptr(cc), float(color_lambda), out.data_ptr(), ldw,
+                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "dss_affinity")
+    return out
+
+
+@torch.no_grad()
+def eigsh_laplacian(W: torch.Tensor, N: int, K: int, lapnorm=True, tol: float = 0.0, max_steps: int = 0
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """W [B, N, ldw] fp32 CUDA -> (eigenvalues [B,K], eigenvectors [B,K,N], info [B,4] int32, resid [B,K])."""
+    _lib.require_cuda(W, "W")
+    lib = _lib.load()
+    assert W.dtype == torch.float32 and W.is_contiguous() and W.dim() == 3 and W.shape[1] == N
+    B, _, ldw = W.shape
+    dev = W.device
+    with torch.cuda.device(dev):
+        evals = torch.empty(B, K, dtype=torch.float32, device=dev)
+        evecs = torch.empty(B, K, N, dtype=torch.float32, device=dev)
+        info = torch.empty(B, 4, dtype=torch.int32, device=dev)
+        resid = torch.empty(B, K, dtype=torch.float32, device=dev)
+        need = int(lib.dss_eigsh_workspace_bytes(B, N, K, max_steps))
+        ws = _scratch.get("eig", need, dev)
+        _lib.check(lib.dss_eigsh_laplacian(W.data_ptr(), ldw, B, N, K, 1 if lapnorm else 0, float(tol), int(max_steps),
+                                           evals.data_ptr(), evecs.data_ptr(), info.data_ptr(), resid.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "dss_eigsh_laplacian")
+    return evals, evecs, info, resid
+
+
+@torch.no_grad()
+def laplacian_eigs(feats: torch.Tensor, K: int, normalize=True, threshold_at_zero=True, lapnorm=True,
+                   rgb_lr: Optional[torch.Tensor] = None, lr_size: Optional[Tuple[int, int]] = None,
+                   color_lambda: float = 0.0, tol: float = 0.0, max_steps: int = 0):
+    """which_matrix='laplacian' of the reference for a batch: feats [B,N,d] -> (eigenvalues [B,K], eigenvectors [B,K,N])."""
+    cc = None
+    if color_lambda > 0:
+        if rgb_lr is None or lr_size is None:
+            raise ValueError("image_color_lambda > 0 needs the low-resolution image (rgb_lr, lr_size)")
+        cc = knn_color_counts(rgb_lr, lr_size[0], lr_size[1])
+    W = affinity(feats, normalize, threshold_at_zero, cc, color_lambda)
+    evals, evecs, info, resid = eigsh_laplacian(W, feats.shape[1], K, lapnorm, tol, max_steps)
+    return evals, evecs, info, resid

@@ -1,0 +1,33 @@
+import importlib
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def dss():
+    """The product package (its directory name has a hyphen, so it is imported by string)."""
+    return importlib.import_module("deep-spectral-segmentation_b200")
+
+
+def load_pkg(sub: str = ""):
+    name = "deep-spectral-segmentation_b200" + (("." + sub) if sub else "")
+    return importlib.import_module(name)
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.set_grad_enabled(False)
+    return torch.device("cuda:0")
