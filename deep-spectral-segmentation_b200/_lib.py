@@ -18,6 +18,10 @@ class VitConfig(C.Structure):
                 ("grid0", c_int), ("ln_eps", c_float)]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_longlong), ("total_ms", C.c_double)]
+
+
 class VitBlockWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b",
                                         "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
@@ -33,6 +37,9 @@ PROTOTYPES = {
     "dss_last_error": (C.c_char_p, []),
     "dss_version": (c_int, []),
     "dss_device_sm_count": (c_int, []),
+    "dss_kernel_launch_count": (C.c_longlong, []),
+    "dss_profile_enable": (None, [c_int]),
+    "dss_profile_read": (c_int, [C.POINTER(ProfileEntry), c_int]),
     "dss_vit_create": (c_int, [C.POINTER(VitConfig), C.POINTER(c_void_p)]),
     "dss_vit_destroy": (None, [c_void_p]),
     "dss_vit_load_weights": (c_int, [c_void_p, C.POINTER(VitWeights), c_void_p]),
@@ -108,3 +115,20 @@ def stream_ptr(device=None) -> int:
 def require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise DssError(f"{name} must be a CUDA tensor: the hot path has no CPU implementation")
+
+
+def launch_count() -> int:
+    return int(load().dss_kernel_launch_count())
+
+
+def profile(enable: bool) -> None:
+    load().dss_profile_enable(1 if enable else 0)
+
+
+def profile_read() -> dict:
+    """{kernel class: (launches, total_ms)} for the recording started by profile(True)."""
+    arr = (ProfileEntry * 32)()
+    n = load().dss_profile_read(arr, 32)
+    if n < 0:
+        check(n, "dss_profile_read")
+    return {arr[i].name.decode(): (int(arr[i].launches), float(arr[i].total_ms)) for i in range(n)}

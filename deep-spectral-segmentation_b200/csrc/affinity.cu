@@ -125,9 +125,13 @@ extern "C" int dss_affinity(const float* feats, int B, int N, int d, int flags, 
       reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + align_up((size_t)B * N * d * sizeof(float), 256));
   DSS_CHECK_CUDA(cudaMemsetAsync(img_max, 0, (size_t)B * sizeof(unsigned int), st));
   const int rows = B * N;
-  rownorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(feats, fn, img_max, rows, N, d, (flags & DSS_AFF_NORMALIZE) ? 1 : 0);
+  {
+    LaunchScope scope(st, KC_ROWNORM);
+    rownorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(feats, fn, img_max, rows, N, d, (flags & DSS_AFF_NORMALIZE) ? 1 : 0);
+  }
   DSS_CHECK_CUDA(cudaGetLastError());
   dim3 grid(cdiv(N, AT), cdiv(N, AT), B);
+  LaunchScope scope(st, KC_AFFINITY);
   affinity_kernel<<<grid, 256, 0, st>>>(fn, img_max, color_counts, color_lambda, Wmat, N, d, ldw,
                                         (flags & DSS_AFF_THRESHOLD_AT_ZERO) ? 1 : 0);
   DSS_CHECK_CUDA(cudaGetLastError());

@@ -40,6 +40,19 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 int device_sm_count();
 
+// ---------------------------------------------------------------- launch accounting / per-class device timing
+enum KernelClass {
+  KC_IM2COL = 0, KC_GEMM_PATCH, KC_CLS_ROW, KC_LAYERNORM, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_PROJ, KC_GEMM_FC1,
+  KC_GEMM_FC2, KC_GEMM_KPROJ, KC_GEMM_OTHER, KC_ROWNORM, KC_AFFINITY, KC_KNN, KC_EIGSH, KC_MISC, KC_COUNT
+};
+// Counts the launch and, when profiling is enabled, brackets it with CUDA events on the launching stream.
+struct LaunchScope {
+  cudaStream_t st;
+  int slot;
+  LaunchScope(cudaStream_t stream, int kernel_class);
+  ~LaunchScope();
+};
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 

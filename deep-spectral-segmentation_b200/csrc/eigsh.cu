@@ -467,6 +467,7 @@ extern "C" int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int
     return DSS_ERR_UNSUPPORTED;
   }
   DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope scope(static_cast<cudaStream_t>(stream), KC_EIGSH);
   lanczos_laplacian_kernel<<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;

@@ -253,7 +253,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols) {
 
 template <int EPI>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& p,
-                     cudaStream_t st) {
+                     cudaStream_t st, int kclass) {
   static bool attr_set = false;
   if (!attr_set) {
     DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -261,6 +261,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
     attr_set = true;
   }
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
+  LaunchScope scope(st, kclass);
   gemm_f16_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, p);
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
@@ -280,17 +281,17 @@ static int check_gemm_args(int M, int N, int K, int epi, const float* bias, cons
 
 // Launch with pre-built tensor maps (used by the ViT forward, which caches them).
 int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* out, int M, int N, int K,
-                int epi, const float* aux, int rin, int rout, cudaStream_t st) {
+                int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass) {
   int rc = check_gemm_args(M, N, K, epi, bias, out, aux, rin, rout);
   if (rc) return rc;
   EpiParams p{out, bias, aux, N, rin, rout};
   switch (epi) {
-    case DSS_EPI_BIAS_F16: return launch_tc<DSS_EPI_BIAS_F16>(tmA, tmB, M, N, K, p, st);
-    case DSS_EPI_BIAS_GELU_F16: return launch_tc<DSS_EPI_BIAS_GELU_F16>(tmA, tmB, M, N, K, p, st);
-    case DSS_EPI_BIAS_RESID_F32: return launch_tc<DSS_EPI_BIAS_RESID_F32>(tmA, tmB, M, N, K, p, st);
-    case DSS_EPI_BIAS_F32: return launch_tc<DSS_EPI_BIAS_F32>(tmA, tmB, M, N, K, p, st);
-    case DSS_EPI_PATCH_F32: return launch_tc<DSS_EPI_PATCH_F32>(tmA, tmB, M, N, K, p, st);
-    case DSS_EPI_DROPCLS_F32: return launch_tc<DSS_EPI_DROPCLS_F32>(tmA, tmB, M, N, K, p, st);
+    case DSS_EPI_BIAS_F16: return launch_tc<DSS_EPI_BIAS_F16>(tmA, tmB, M, N, K, p, st, kclass);
+    case DSS_EPI_BIAS_GELU_F16: return launch_tc<DSS_EPI_BIAS_GELU_F16>(tmA, tmB, M, N, K, p, st, kclass);
+    case DSS_EPI_BIAS_RESID_F32: return launch_tc<DSS_EPI_BIAS_RESID_F32>(tmA, tmB, M, N, K, p, st, kclass);
+    case DSS_EPI_BIAS_F32: return launch_tc<DSS_EPI_BIAS_F32>(tmA, tmB, M, N, K, p, st, kclass);
+    case DSS_EPI_PATCH_F32: return launch_tc<DSS_EPI_PATCH_F32>(tmA, tmB, M, N, K, p, st, kclass);
+    case DSS_EPI_DROPCLS_F32: return launch_tc<DSS_EPI_DROPCLS_F32>(tmA, tmB, M, N, K, p, st, kclass);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return DSS_ERR_BAD_ARG;
@@ -300,6 +301,7 @@ template <int EPI>
 static int launch_simt(const void* A, const void* Wt, int M, int N, int K, const EpiParams& p, cudaStream_t st) {
   dim3 block(4, 32);
   dim3 grid(cdiv(N / 32, 4), cdiv(M, 32));
+  LaunchScope scope(st, KC_MISC);
   gemm_f16_simt_kernel<EPI><<<grid, block, 0, st>>>(reinterpret_cast<const __half*>(A),
                                                     reinterpret_cast<const __half*>(Wt), M, N, K, p);
   DSS_CHECK_CUDA(cudaGetLastError());
@@ -318,7 +320,8 @@ extern "C" int dss_op_gemm_f16(const void* A, const void* Wt, const float* bias,
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_f16(&tmA, A, M, K))) return rc;
   if ((rc = make_tmap_f16(&tmB, Wt, N, K))) return rc;
-  return gemm_f16_tc(tmA, tmB, bias, out, M, N, K, epilogue, aux, rin, rout, static_cast<cudaStream_t>(stream));
+  return gemm_f16_tc(tmA, tmB, bias, out, M, N, K, epilogue, aux, rin, rout, static_cast<cudaStream_t>(stream),
+                     KC_GEMM_OTHER);
 }
 
 extern "C" int dss_op_gemm_f16_simt(const void* A, const void* Wt, const float* bias, void* out, int M, int N, int K,

@@ -109,6 +109,7 @@ extern "C" int dss_knn_color_counts(const float* rgb, int B, int Hl, int Wl, uin
   const int ks[2] = {20, 10};
   const double ws_[2] = {2.0, 0.1};
   for (int pass = 0; pass < 2; ++pass) {
+    LaunchScope scope(st, KC_KNN);
     knn_counts_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(rgb, reinterpret_cast<uint32_t*>(counts), N, Hl, Wl, ks[pass],
                                                           ws_[pass]);
     DSS_CHECK_CUDA(cudaGetLastError());

@@ -20,7 +20,7 @@ namespace dss {
 
 int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols);
 int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* out, int M, int N, int K,
-                int epi, const float* aux, int rin, int rout, cudaStream_t st);
+                int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass);
 int launch_im2col(const uint8_t* img, void* patches, int B, int H, int W, int P, cudaStream_t st);
 int launch_cls_row(float* x, const float* cls, const float* pos, int B, int T, int d, cudaStream_t st);
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int M, int d, float eps, cudaStream_t st);
@@ -184,31 +184,35 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
 
   // tokens: x[b, 1+n, :] = patch_embed + pos ; x[b, 0, :] = cls + pos[0]
   if ((rc = launch_im2col(img, w.patches, B, H, W, P, st))) return rc;
-  if ((rc = gemm_f16_tc(tm_patches, h->tm_patch, h->patch_b, w.x, B * Np, d, Kp, DSS_EPI_PATCH_F32, pos, Np, T, st)))
+  if ((rc = gemm_f16_tc(tm_patches, h->tm_patch, h->patch_b, w.x, B * Np, d, Kp, DSS_EPI_PATCH_F32, pos, Np, T, st,
+                        KC_GEMM_PATCH)))
     return rc;
   if ((rc = launch_cls_row(w.x, h->cls, pos, B, T, d, st))) return rc;
 
   for (int l = 0; l < n_full; ++l) {
     const BlockW& bw = h->blocks[l];
     if ((rc = launch_layernorm(w.x, bw.ln1_w, bw.ln1_b, w.xn, M, d, c.ln_eps, st))) return rc;
-    if ((rc = gemm_f16_tc(tm_xn, bw.tm_qkv, bw.qkv_b, w.qkv, M, 3 * d, d, DSS_EPI_BIAS_F16, nullptr, 0, 0, st)))
+    if ((rc = gemm_f16_tc(tm_xn, bw.tm_qkv, bw.qkv_b, w.qkv, M, 3 * d, d, DSS_EPI_BIAS_F16, nullptr, 0, 0, st,
+                          KC_GEMM_QKV)))
       return rc;
     if ((rc = launch_attention(w.qkv, w.attn, B, T, c.heads, st))) return rc;
-    if ((rc = gemm_f16_tc(tm_attn, bw.tm_proj, bw.proj_b, w.x, M, d, d, DSS_EPI_BIAS_RESID_F32, nullptr, 0, 0, st)))
+    if ((rc = gemm_f16_tc(tm_attn, bw.tm_proj, bw.proj_b, w.x, M, d, d, DSS_EPI_BIAS_RESID_F32, nullptr, 0, 0, st,
+                          KC_GEMM_PROJ)))
       return rc;
     if ((rc = launch_layernorm(w.x, bw.ln2_w, bw.ln2_b, w.xn, M, d, c.ln_eps, st))) return rc;
     if ((rc = gemm_f16_tc(tm_xn, bw.tm_fc1, bw.fc1_b, w.hid, M, c.mlp_ratio * d, d, DSS_EPI_BIAS_GELU_F16, nullptr, 0,
-                          0, st)))
+                          0, st, KC_GEMM_FC1)))
       return rc;
     if ((rc = gemm_f16_tc(tm_hid, bw.tm_fc2, bw.fc2_b, w.x, M, d, c.mlp_ratio * d, DSS_EPI_BIAS_RESID_F32, nullptr, 0,
-                          0, st)))
+                          0, st, KC_GEMM_FC2)))
       return rc;
   }
   if (k_proj) {
     const BlockW& bw = h->blocks[n_full];
     if ((rc = launch_layernorm(w.x, bw.ln1_w, bw.ln1_b, w.xn, M, d, c.ln_eps, st))) return rc;
     // K third of the qkv projection (weight rows [d, 2d)), CLS rows dropped: out[b, n, :] == qkv[b, 1+n, d:2d]
-    if ((rc = gemm_f16_tc(tm_xn, bw.tm_k, bw.qkv_b + d, out, M, d, d, DSS_EPI_DROPCLS_F32, nullptr, T, Np, st)))
+    if ((rc = gemm_f16_tc(tm_xn, bw.tm_k, bw.qkv_b + d, out, M, d, d, DSS_EPI_DROPCLS_F32, nullptr, T, Np, st,
+                          KC_GEMM_KPROJ)))
       return rc;
   } else {
     DSS_CHECK_CUDA(cudaMemcpyAsync(out, w.x, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -269,6 +273,7 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
   uint8_t* base = reinterpret_cast<uint8_t*>(h->arena);
   auto cvt = [&](const float* src, size_t o, size_t n) -> int {
     DSS_REQUIRE(src, "vit_load_weights: null weight pointer");
+    LaunchScope scope(st, KC_MISC);
     f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<__half*>(base + o), n);
     DSS_CHECK_CUDA(cudaGetLastError());
     return DSS_OK;

@@ -274,6 +274,7 @@ int launch_im2col(const uint8_t* img, void* patches, int B, int H, int W, int P,
   DSS_REQUIRE(B > 0 && Hp > 0 && Wp > 0, "im2col: image %dx%d smaller than one patch", H, W);
   const long long total = (long long)B * Hp * Wp * 3 * P * (P / 8);
   const int threads = 256;
+  LaunchScope scope(st, KC_IM2COL);
   im2col_f16_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
       img, reinterpret_cast<__half*>(patches), B, H, W, P, Hp, Wp);
   DSS_CHECK_CUDA(cudaGetLastError());
@@ -281,6 +282,7 @@ int launch_im2col(const uint8_t* img, void* patches, int B, int H, int W, int P,
 }
 
 int launch_cls_row(float* x, const float* cls, const float* pos, int B, int T, int d, cudaStream_t st) {
+  LaunchScope scope(st, KC_CLS_ROW);
   cls_row_kernel<<<cdiv(B * d, 256), 256, 0, st>>>(x, cls, pos, B, T, d);
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
@@ -292,6 +294,7 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* y, in
   DSS_REQUIRE(M > 0, "layernorm: empty input");
   const int threads = 256;  // 8 rows per CTA
   const int grid = cdiv(M, threads / 32);
+  LaunchScope scope(st, KC_LAYERNORM);
   if (d == 384)
     layernorm_f16_kernel<384><<<grid, threads, 0, st>>>(x, g, b, reinterpret_cast<__half*>(y), M, eps);
   else
@@ -303,6 +306,7 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* y, in
 int launch_attention(const void* qkv, void* out, int B, int T, int heads, cudaStream_t st) {
   DSS_REQUIRE(B > 0 && T > 0 && heads > 0, "attention: empty problem");
   dim3 grid(cdiv(T, ATT_BM), heads, B);
+  LaunchScope scope(st, KC_ATTENTION);
   attention_f16_kernel<<<grid, ATT_THREADS, 0, st>>>(reinterpret_cast<const __half*>(qkv),
                                                      reinterpret_cast<__half*>(out), T, heads);
   DSS_CHECK_CUDA(cudaGetLastError());

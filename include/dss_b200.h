@@ -39,6 +39,15 @@ const char* dss_last_error(void);
 int dss_version(void);            /* 100 * major + minor */
 int dss_device_sm_count(void);    /* SM count of the current device (148 on B200), <0 on error */
 
+/* Launch accounting: number of kernels this library has launched in this process. */
+long long dss_kernel_launch_count(void);
+/* Per-kernel-class device timing for roofline reports: while enabled, every kernel launch is bracketed by CUDA
+ * events on its stream. dss_profile_enable(1) starts a fresh recording, dss_profile_read synchronises the recorded
+ * events and returns the number of classes written to `out` (<0 on error). Not for use inside timed regions. */
+typedef struct { const char* name; long long launches; double total_ms; } dss_profile_entry;
+void dss_profile_enable(int on);
+int dss_profile_read(dss_profile_entry* out, int max_entries);
+
 /* ------------------------------------------------------------------------------------------------------------
  * DINO ViT feature extractor  (replaces utils.get_model + model.get_intermediate_layers + the qkv hook,
  * extract/extract_utils.py:40-50, extract/extract.py:49-53,82-98)

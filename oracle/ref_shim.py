@@ -13,6 +13,7 @@ With no GPU, ``Tensor.cuda`` (extract.py:146) is made a no-op so the matmul runs
 """
 from __future__ import annotations
 
+import importlib.machinery
 import sys
 import types
 from pathlib import Path
@@ -29,6 +30,7 @@ def available() -> bool:
 
 def _stub(name, **attrs):
     m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)  # keeps importlib.util.find_spec(name) happy
     for k, v in attrs.items():
         setattr(m, k, v)
     sys.modules[name] = m
@@ -50,15 +52,18 @@ def load_reference():
     def _never(*a, **k):
         raise RuntimeError("stubbed dependency called")
 
+    transient = []  # stubs only needed while the reference's top-level imports run (removed again afterwards so
+    #                 that other libraries probing e.g. `accelerate` do not mistake them for the real packages)
     if "fire" not in sys.modules:
-        _stub("fire", Fire=_never)
+        _stub("fire", Fire=_never); transient.append("fire")
     if "accelerate" not in sys.modules:
-        _stub("accelerate", Accelerator=_never)
+        _stub("accelerate", Accelerator=_never); transient.append("accelerate")
     try:
         import skimage.morphology  # noqa: F401
     except Exception:
         _stub("skimage")
         _stub("skimage.morphology", binary_dilation=_never, binary_erosion=_never)
+        transient += ["skimage", "skimage.morphology"]
     try:
         import pymatting  # noqa: F401
     except Exception:
@@ -73,6 +78,8 @@ def load_reference():
         import extract as ref_extract  # the reference's module, unmodified
     finally:
         sys.path.remove(str(REFERENCE_DIR))
+        for name in transient:
+            sys.modules.pop(name, None)
     _ref = ref_extract
     return _ref
 

@@ -1,0 +1,126 @@
+"""CPU suite: host-side logic that mirrors the reference's CLI / file contract (no compute calls)."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_pkg
+
+
+def test_fire_compatible_parser():
+    cli = load_pkg("cli")
+    ex = load_pkg("extract")
+    args, kw = cli.parse_args(ex.extract_eigs, ["--images_root", "imgs", "--features_dir=feat", "--output_dir", "out",
+                                               "--which_matrix", "laplacian", "--K", "5", "--nolapnorm",
+                                               "--image_color_lambda", "10.0", "--normalize", "False",
+                                               "--image_downsample_factor", "None"])
+    assert args == [] and kw == {"images_root": "imgs", "features_dir": "feat", "output_dir": "out",
+                                 "which_matrix": "laplacian", "K": 5, "lapnorm": False, "image_color_lambda": 10.0,
+                                 "normalize": False, "image_downsample_factor": None}
+    args, kw = cli.parse_args(ex.extract_features, ["list.txt", "root", "--model_name", "dino_vits16", "--batch_size=1",
+                                                   "--output_dir", "o", "--which_block", "-1"])
+    assert args == ["list.txt", "root"] and kw["which_block"] == -1 and kw["batch_size"] == 1
+    with pytest.raises(SystemExit):
+        cli.parse_args(ex.extract_eigs, ["--no_such_flag", "1"])
+    with pytest.raises(SystemExit):
+        cli.Fire({"extract_eigs": ex.extract_eigs}, ["bogus_command"])
+    assert cli.Fire({"f": lambda a, b=2: (a, b)}, ["f", "3", "--b", "[1,2]"]) == (3, [1, 2])
+
+
+def test_signatures_match_reference_contract():
+    """Argument names / defaults of the reference's callables (extract/extract.py:21-28,119-132,247-261)."""
+    import inspect
+    ex = load_pkg("extract")
+    p = inspect.signature(ex.extract_features).parameters
+    assert list(p)[:6] == ["images_list", "images_root", "model_name", "batch_size", "output_dir", "which_block"]
+    assert p["which_block"].default == -1
+    p = inspect.signature(ex.extract_eigs).parameters
+    want = {"which_matrix": "laplacian", "which_color_matrix": "knn", "which_features": "k", "normalize": True,
+            "threshold_at_zero": True, "lapnorm": True, "K": 20, "image_downsample_factor": None,
+            "image_color_lambda": 0.0, "multiprocessing": 0}
+    assert list(p)[:3] == ["images_root", "features_dir", "output_dir"]
+    for k, v in want.items():
+        assert p[k].default == v, k
+    p = inspect.signature(ex._extract_eig).parameters
+    assert list(p)[:4] == ["inp", "K", "images_root", "output_dir"] and p["image_color_lambda"].default == 10
+
+
+def test_images_dataset_and_sizes(tmp_path):
+    utils = load_pkg("extract_utils")
+    synth = load_pkg("synth")
+    from PIL import Image
+    for name, seed in (("b.png", 1), ("a.png", 2)):
+        Image.fromarray(synth.blobs_image(50, 70, seed).numpy()).save(tmp_path / name)
+    ds = utils.ImagesDataset(["b.png", "a.png", "b.png"], images_root=str(tmp_path))
+    assert ds.filenames == ["a.png", "b.png"] and len(ds) == 2          # de-duplicated + sorted (extract_utils.py:23)
+    img, path, idx = ds[0]
+    assert path == "a.png" and idx == 0 and img.dtype == torch.uint8 and tuple(img.shape) == (50, 70, 3)
+    assert torch.equal(img, synth.blobs_image(50, 70, 2))               # RGB order, lossless png
+    d = {"patch_size": 16, "shape": (1, 3, 250, 333)}
+    assert utils.get_image_sizes(d) == (1, 3, 250, 333, 16, 15, 20, 240, 320)
+    assert utils.get_image_sizes(d, 8)[4:] == (8, 31, 41, 248, 328)
+
+
+def test_make_output_dir_non_interactive(tmp_path, monkeypatch):
+    utils = load_pkg("extract_utils")
+    out = tmp_path / "a" / "b"
+    utils.make_output_dir(out)
+    assert out.is_dir()
+    (out / "x.pth").write_text("x")
+    utils.make_output_dir(out, assume_yes=True)           # explicit yes
+    monkeypatch.setattr(sys.stdin, "isatty", lambda: False, raising=False)
+    utils.make_output_dir(out)                             # non-tty: continues instead of blocking on input()
+    monkeypatch.setattr(sys.stdin, "isatty", lambda: True, raising=False)
+    monkeypatch.setattr("builtins.input", lambda *_: "n")
+    with pytest.raises(SystemExit):
+        utils.make_output_dir(out)                         # interactive "n" exits like the reference
+
+
+def test_feature_dict_layout_roundtrips_through_torch_load(tmp_path):
+    ex = load_pkg("extract")
+    utils = load_pkg("extract_utils")
+    k = torch.randn(1, 20 * 15, 384)
+    d = ex._feature_dict(k, 7, "sub/img_0007.jpg", "dino_vits16", 16, 250, 333)
+    torch.save(d, tmp_path / "f.pth")
+    back = torch.load(tmp_path / "f.pth", map_location="cpu")   # weights_only default: the layout must stay loadable
+    assert set(back) == {"k", "indices", "file", "id", "model_name", "patch_size", "shape"}
+    assert back["id"] == "img_0007" and back["file"][:-4] == "sub/img_0007" and back["indices"].item() == 7
+    assert back["indices"].dim() == 0 and back["shape"] == (1, 3, 250, 333) and back["k"].shape == (1, 300, 384)
+    assert utils.get_image_sizes(back)[5:7] == (15, 20)
+
+
+def test_random_state_dict_is_loadable_by_the_oracle_and_deterministic():
+    from oracle import dino_vit
+    vit = load_pkg("vit")
+    sd = vit.random_state_dict("dino_vits16", 0)
+    sd2 = vit.random_state_dict("dino_vits16", 0)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+    m = dino_vit.DinoViT(dino_vit.cfg_for("dino_vits16"))
+    m.load_state_dict(sd)                                   # same parameter names and shapes as upstream
+    assert set(vit.flat_param_order("dino_vits16")) == set(sd) - {"norm.weight", "norm.bias"}
+    assert sum(v.numel() for v in sd.values()) == sum(p.numel() for p in m.parameters())
+    w = sd["blocks.3.attn.qkv.weight"]
+    assert abs(w.std().item() - 0.02) < 2e-3 and w.abs().max().item() <= 2.0 + 1e-6
+
+
+def test_shard_indices_cover_everything_once():
+    pl = load_pkg("pipeline")
+    for n, world in [(10, 1), (10, 3), (50_000, 8), (5, 8)]:
+        parts = [pl.shard_indices(n, r, world) for r in range(world)]
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    with pytest.raises(ValueError):
+        pl.shard_indices(10, 3, 2)
+
+
+def test_synthetic_inputs_are_seeded():
+    synth = load_pkg("synth")
+    a, b = synth.blobs_image(64, 80, 5), synth.blobs_image(64, 80, 5)
+    assert torch.equal(a, b) and a.dtype == torch.uint8 and tuple(a.shape) == (64, 80, 3)
+    assert not torch.equal(a, synth.blobs_image(64, 80, 6))
+    shapes = synth.voc_shapes(1000, 0)
+    assert shapes == synth.voc_shapes(1000, 0) and max(max(s) for s in shapes) == 500
+    f = synth.structured_features(100, 32, 4, 1)
+    assert torch.equal(f, synth.structured_features(100, 32, 4, 1)) and f.dtype == torch.float32

@@ -1,0 +1,57 @@
+"""-m gpu: the CUDA path against the committed golden vectors, i.e. the outputs of the reference's OWN _extract_eig
+(run in the dev container by oracle/make_golden.py) -- including the colour-KNN branch and the non-default flags."""
+import ast
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_pkg
+from test_cpu_oracle import GOLDEN, _aligned_err, gap_tolerance, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[p.stem for p in GOLDEN])
+def test_cuda_path_reproduces_reference_outputs(cuda, path):
+    spectral = load_pkg("spectral")
+    z, kw = load_golden(path)
+    feats = torch.from_numpy(z["feats"])
+    K = int(z["K"])
+    lam = float(kw.get("image_color_lambda", 0.0))
+    rgb, lr_size = None, None
+    if lam > 0:
+        lr = z["image_lr"]
+        lr_size = (lr.shape[0], lr.shape[1])
+        rgb = torch.from_numpy(lr.reshape(1, -1, 3).astype(np.float32)).to(cuda)
+    ev, vec, info, _ = spectral.laplacian_eigs(feats[None].to(cuda), K, kw.get("normalize", True),
+                                               kw.get("threshold_at_zero", True), kw.get("lapnorm", True), rgb, lr_size, lam)
+    torch.cuda.synchronize()
+    assert int(info[0, 1]) == 1
+    ev, vec = ev[0].cpu().numpy(), vec[0].cpu().numpy()
+    scale = max(1.0, float(np.abs(z["eigenvalues"]).max()))
+    assert np.abs(ev - z["eigenvalues"]).max() <= 1e-5 * scale
+    err = _aligned_err(vec, z["eigenvectors"])
+    tol = np.maximum(1e-4, gap_tolerance(feats, K, kw))  # 1e-4, widened only where the reference itself jitters more
+    print(path.stem, "rel-L2 vs reference:", err, "tol", tol)
+    assert np.all(err <= tol)
+    for k in range(K):                                   # same sign convention as the reference (extract.py:237-240)
+        m = float((vec[k] > 0).mean())
+        assert not (0.5 < m < 1.0)
+        if float((z["eigenvectors"][k] > 0).mean()) not in (0.0, 0.5, 1.0):
+            assert np.dot(vec[k], z["eigenvectors"][k]) > 0
+
+
+def test_knn_counts_match_reference_sparse_matrix(cuda):
+    from oracle import eigs_ref
+    spectral = load_pkg("spectral")
+    for path in GOLDEN:
+        z, kw = load_golden(path)
+        if not kw.get("image_color_lambda", 0):
+            continue
+        lr = z["image_lr"]
+        want = eigs_ref.knn_affinity(lr).toarray()
+        rgb = torch.from_numpy(lr.reshape(1, -1, 3).astype(np.float32)).to(cuda)
+        got = spectral.knn_color_counts(rgb, lr.shape[0], lr.shape[1])[0].cpu().numpy()
+        assert got.dtype == np.uint8 and np.array_equal(got.astype(np.float64), want), path.stem
