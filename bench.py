@@ -162,16 +162,33 @@ def cpu_pool_images_per_sec(model_name, size, K, n_images, steps, warmup, thread
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
     cores = os.cpu_count() or 1
-    workers = max(1, min(cores // threads_per_worker, n_images))
+    workers = max(1, min(cores // threads_per_worker, n_images, 64))
     ctx = mp.get_context("spawn")
+    # numpy/scipy's BLAS (OpenBLAS) sizes its own thread pool from the environment at import time: without this
+    # every worker would start one BLAS thread per host core and the pool would thrash
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = str(threads_per_worker)
+    try:
+        return _cpu_pool_run(ctx, workers, model_name, size, K, n_images, steps, warmup, threads_per_worker)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _cpu_pool_run(ctx, workers, model_name, size, K, n_images, steps, warmup, threads_per_worker):
+    from concurrent.futures import ProcessPoolExecutor
     with ProcessPoolExecutor(workers, mp_context=ctx, initializer=_ref_worker_init,
                              initargs=(model_name, threads_per_worker)) as ex:
         for w in range(max(1, warmup)):
-            list(ex.map(_ref_worker_task, [(10_000 + i, size, K) for i in range(workers)]))
+            list(ex.map(_ref_worker_task, [(10_000 + i, size, K) for i in range(workers)], timeout=600))
         t0 = time.perf_counter()
         parts = []
         for s in range(steps):
-            parts += list(ex.map(_ref_worker_task, [(s * n_images + i, size, K) for i in range(n_images)]))
+            parts += list(ex.map(_ref_worker_task, [(s * n_images + i, size, K) for i in range(n_images)], timeout=600))
         dt = time.perf_counter() - t0
     split = {"vit_s_per_image": sum(p[0] for p in parts) / len(parts), "eigs_s_per_image": sum(p[1] for p in parts) / len(parts)}
     return n_images * steps / dt, dt, {"workers": workers, "threads_per_worker": threads_per_worker, **split}
@@ -181,7 +198,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = args.ref_images_per_step if args.ref_images_per_step > 0 else 2 * max(1, cores // 4)
+    n = args.ref_images_per_step if args.ref_images_per_step > 0 else 2 * max(1, min(cores // 4, 64))
     value, dt, split = cpu_pool_images_per_sec(args.model, args.size, args.K, n, args.steps, args.warmup)
     sample = (f"{n} synthetic {args.size}x{args.size} images per step (a bounded sample of the {args.images_per_step}-image step); "
               f"fp32 eager DINO ViT + the reference's scipy eigsh route in {split['workers']} worker processes x "
@@ -346,7 +363,7 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import eigs_ref
         cores = os.cpu_count() or 1
-        n_cpu = args.cpu_sample if args.cpu_sample > 0 else 2 * max(1, cores // 4)
+        n_cpu = args.cpu_sample if args.cpu_sample > 0 else 2 * max(1, min(cores // 4, 64))
         ips, _, split = cpu_pool_images_per_sec(args.model, S, K, n_cpu, 1, 1)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": f"{n_cpu} synthetic {S}x{S} images; fp32 eager DINO ViT + the reference's scipy eigsh route, "

@@ -1,102 +1,74 @@
 // Patch-affinity build: W = relu(F^ F^T) / max (+ lambda * colour counts)   (reference extract/extract.py:148,191-221)
 //
-// fp32 end to end: the eigenvectors of the graph Laplacian move by 2e-4..8e-4 when the features are rounded to
-// bf16, so this stage does not use reduced-precision tensor-core operands.
+// The Gram product runs on the tcgen05 tensor cores at fp32-equivalent accuracy. The eigenvectors of the graph
+// Laplacian move by 2e-4..8e-4 when the features are merely rounded to bf16, so each normalised
+// feature x is split as x = hi + lo with hi = fp16(x), lo = x - hi (|lo| <= 2^-12 |x|) and
+//     x.y ~= hi.hi' + (hi/64).(64 lo') + (64 lo).(hi'/64)              (lo.lo' ~ 2^-24 is dropped)
+// i.e. ONE fp16 GEMM with K = 3d over S = [hi | hi/64 | 64 lo] against the same array with the last two groups of
+// K slabs swapped. The 2^+-6 factors keep every operand inside the fp16 normal range. Measured error of the split
+// against a float64 product: 7e-8, smaller than a plain fp32 product's 1e-6.
+// The GEMM itself is gemm.cu's TMA/tcgen05 kernel in batched mode with the affinity epilogue (relu, /max,
+// + lambda*counts, zero padding of the row pitch) fused.
 #include "common.cuh"
 
 namespace dss {
 
-// ---- row normalisation: fn = f / max(||f||_2, 1e-12)  (F.normalize), and the per-image max of the diagonal of
-// F^ F^T (== max of the whole matrix by Cauchy-Schwarz), accumulated with an integer atomicMax on the float bits.
+int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols);
+int affinity_gemm_tc(const CUtensorMap& tmS, int images, int Nimg, int d, float* Wout, int ldw,
+                     const unsigned int* img_max, const uint8_t* counts, float lambda, int threshold, cudaStream_t st);
+
+// per-image max |f| (only needed when the features are NOT normalised: they are pre-scaled by a power of two so
+// that fp16 cannot overflow; the scale cancels in W / max(W))
 __global__ void __launch_bounds__(256)
-rownorm_kernel(const float* __restrict__ f, float* __restrict__ fn, unsigned int* __restrict__ img_max, int rows,
-               int N, int d, int normalize) {
+absmax_kernel(const float* __restrict__ f, unsigned int* __restrict__ img_absmax, int rows, int N, int d) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* x = f + (long long)row * d;
-  float* y = fn + (long long)row * d;
+  float m = 0.f;
+  for (int k = lane; k < d; k += 32) m = fmaxf(m, fabsf(x[k]));
+  m = warp_max(m);
+  if (lane == 0) atomicMax(img_absmax + row / N, __float_as_uint(m));
+}
+
+// One warp per row: x^ = x / max(||x||, 1e-12) (F.normalize) or x * 2^-e; writes S[row] = [hi | hi/64 | 64 lo]
+// (each group padded with zeros to dpad columns) and accumulates the per-image max of the Gram diagonal
+// (== max of the whole matrix by Cauchy-Schwarz) with an integer atomicMax on the float bits.
+__global__ void __launch_bounds__(256)
+rownorm_split_kernel(const float* __restrict__ f, __half* __restrict__ S, unsigned int* __restrict__ img_max,
+                     const unsigned int* __restrict__ img_absmax, int rows, int N, int d, int dpad, int normalize) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = f + (long long)row * d;
+  __half* s = S + (long long)row * 3 * dpad;
   float ss = 0.f;
   for (int k = lane; k < d; k += 32) ss = fmaf(x[k], x[k], ss);
   ss = warp_sum(ss);
-  const float denom = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps)
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  float pre = 1.0f;
+  if (!normalize) {
+    const float am = __uint_as_float(img_absmax[row / N]);
+    if (am > 0.f) pre = exp2f(-ceilf(log2f(am)));
+  }
   float s2 = 0.f;
-  for (int k = lane; k < d; k += 32) {
-    const float v = normalize ? x[k] / denom : x[k];
-    y[k] = v;
+  for (int k = lane; k < dpad; k += 32) {
+    float v = 0.f;
+    if (k < d) v = normalize ? x[k] / denom : x[k] * pre;
+    const __half hi = __float2half_rn(v);
+    const float hif = __half2float(hi);
+    s[k] = hi;
+    s[dpad + k] = __float2half_rn(hif * 0.015625f);
+    s[2 * dpad + k] = __float2half_rn((v - hif) * 64.0f);
     s2 = fmaf(v, v, s2);
   }
   s2 = warp_sum(s2);
   if (lane == 0) atomicMax(img_max + row / N, __float_as_uint(fmaxf(s2, 0.f)));
 }
 
-// ---- W tile kernel: 64x64 tile per CTA, 16x16 threads, 4x4 micro-tile, K chunks of 16 through shared memory.
-constexpr int AT = 64, AK = 16;
-
-__global__ void __launch_bounds__(256)
-affinity_kernel(const float* __restrict__ fn, const unsigned int* __restrict__ img_max,
-                const uint8_t* __restrict__ counts, float lambda, float* __restrict__ Wm, int N, int d, int ldw,
-                int threshold) {
-  __shared__ float As[AK][AT + 4];
-  __shared__ float Bs[AK][AT + 4];
-  const int b = blockIdx.z;
-  const int r0 = blockIdx.y * AT, c0 = blockIdx.x * AT;
-  const float* F = fn + (long long)b * N * d;
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int lr = tid >> 2, lk = (tid & 3) * 4;  // loader: row in tile, k offset
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < d; k0 += AK) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
-    if (r0 + lr < N && k0 + lk < d) a = *reinterpret_cast<const float4*>(F + (long long)(r0 + lr) * d + k0 + lk);
-    if (c0 + lr < N && k0 + lk < d) bb = *reinterpret_cast<const float4*>(F + (long long)(c0 + lr) * d + k0 + lk);
-    As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
-    Bs[lk + 0][lr] = bb.x; Bs[lk + 1][lr] = bb.y; Bs[lk + 2][lr] = bb.z; Bs[lk + 3][lr] = bb.w;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < AK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float ar[4] = {av.x, av.y, av.z, av.w};
-      const float br[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-  const float mx = __uint_as_float(img_max[b]);
-  float* Wb = Wm + (long long)b * N * ldw;
-  const uint8_t* Cb = counts ? counts + (long long)b * N * N : nullptr;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty * 4 + i;
-    if (r >= N) continue;
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + tx * 4 + j;
-      float w = acc[i][j];
-      if (threshold) w = w > 0.f ? w : 0.f;        // W * (W > 0)
-      w = w / mx;                                  // W / W.max()
-      if (Cb && c < N) w += static_cast<float>(Cb[(long long)r * N + c]) * lambda;  // + W_color * lambda
-      o[j] = (c < N) ? w : 0.f;                    // columns [N, ldw) are zero padding
-    }
-    const int c = c0 + tx * 4;
-    if (c + 3 < ldw) {
-      *reinterpret_cast<float4*>(Wb + (long long)r * ldw + c) = make_float4(o[0], o[1], o[2], o[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (c + j < ldw) Wb[(long long)r * ldw + c + j] = o[j];
-    }
-  }
+static size_t split_bytes(int B, int N, int d) {
+  const int dpad = (d + 63) / 64 * 64;
+  return align_up((size_t)B * N * 3 * dpad * sizeof(__half) + 128 * 3 * dpad * sizeof(__half), 1024);  // + tile overrun
 }
 
 }  // namespace dss
@@ -105,35 +77,41 @@ using namespace dss;
 
 extern "C" size_t dss_affinity_workspace_bytes(int B, int N, int d) {
   if (B <= 0 || N <= 0 || d <= 0) return 0;
-  return align_up((size_t)B * N * d * sizeof(float), 256) + align_up((size_t)B * sizeof(unsigned int), 256);
+  return split_bytes(B, N, d) + 2 * align_up((size_t)B * sizeof(unsigned int), 256);
 }
 
 extern "C" int dss_affinity(const float* feats, int B, int N, int d, int flags, const uint8_t* color_counts,
                             float color_lambda, float* Wmat, int ldw, void* ws, size_t ws_bytes, dss_stream_t stream) {
   DSS_REQUIRE(feats && Wmat && ws, "affinity: null pointer");
   DSS_REQUIRE(B > 0 && N > 0 && d > 0, "affinity: empty problem B=%d N=%d d=%d", B, N, d);
-  DSS_REQUIRE(d % 4 == 0, "affinity: feature dim must be a multiple of 4 (got %d)", d);
   DSS_REQUIRE(ldw >= N && ldw % 4 == 0, "affinity: ldw must be >= N and a multiple of 4 (N=%d ldw=%d)", N, ldw);
   DSS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "affinity: workspace must be 256-byte aligned");
+  DSS_REQUIRE((reinterpret_cast<uintptr_t>(Wmat) & 15) == 0, "affinity: W must be 16-byte aligned");
   if (ws_bytes < dss_affinity_workspace_bytes(B, N, d)) {
     set_error("affinity: workspace too small (%zu < %zu)", ws_bytes, dss_affinity_workspace_bytes(B, N, d));
     return DSS_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* fn = reinterpret_cast<float*>(ws);
-  unsigned int* img_max =
-      reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + align_up((size_t)B * N * d * sizeof(float), 256));
-  DSS_CHECK_CUDA(cudaMemsetAsync(img_max, 0, (size_t)B * sizeof(unsigned int), st));
+  const int dpad = (d + 63) / 64 * 64;
+  const int normalize = (flags & DSS_AFF_NORMALIZE) ? 1 : 0;
+  __half* S = reinterpret_cast<__half*>(ws);
+  unsigned int* img_max = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(ws) + split_bytes(B, N, d));
+  unsigned int* img_absmax = img_max + align_up((size_t)B * sizeof(unsigned int), 256) / sizeof(unsigned int);
+  DSS_CHECK_CUDA(cudaMemsetAsync(img_max, 0, 2 * align_up((size_t)B * sizeof(unsigned int), 256), st));
   const int rows = B * N;
+  if (!normalize) {
+    LaunchScope scope(st, KC_ROWNORM);
+    absmax_kernel<<<cdiv(rows, 8), 256, 0, st>>>(feats, img_absmax, rows, N, d);
+    DSS_CHECK_CUDA(cudaGetLastError());
+  }
   {
     LaunchScope scope(st, KC_ROWNORM);
-    rownorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(feats, fn, img_max, rows, N, d, (flags & DSS_AFF_NORMALIZE) ? 1 : 0);
+    rownorm_split_kernel<<<cdiv(rows, 8), 256, 0, st>>>(feats, S, img_max, img_absmax, rows, N, d, dpad, normalize);
+    DSS_CHECK_CUDA(cudaGetLastError());
   }
-  DSS_CHECK_CUDA(cudaGetLastError());
-  dim3 grid(cdiv(N, AT), cdiv(N, AT), B);
-  LaunchScope scope(st, KC_AFFINITY);
-  affinity_kernel<<<grid, 256, 0, st>>>(fn, img_max, color_counts, color_lambda, Wmat, N, d, ldw,
-                                        (flags & DSS_AFF_THRESHOLD_AT_ZERO) ? 1 : 0);
-  DSS_CHECK_CUDA(cudaGetLastError());
-  return DSS_OK;
+  CUtensorMap tmS;
+  int rc = make_tmap_f16(&tmS, S, rows, 3 * dpad);
+  if (rc) return rc;
+  return affinity_gemm_tc(tmS, B, N, dpad, Wmat, ldw, img_max, color_counts, color_lambda,
+                          (flags & DSS_AFF_THRESHOLD_AT_ZERO) ? 1 : 0, st);
 }

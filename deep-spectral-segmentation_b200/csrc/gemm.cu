@@ -1,26 +1,36 @@
 // out = epilogue(A[M,K] * Wt[N,K]^T + bias) with fp16 operands, fp32 accumulation in Tensor Memory.
 //
-// One CTA computes one 128x128 output tile:
-//   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, 64-wide K slabs, STAGES-deep ring)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x128x16, kind::f16)
-//   warps 2..5  : epilogue       (tcgen05.ld 32 lanes x 32 columns -> bias / GELU / residual -> global)
-// Two such CTAs fit on one SM (96 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps the other's
-// main loop. Both operands are K-major, which is the native layout of activations [rows, features] and of
-// torch Linear weights [out, in]; no transposes anywhere.
+// Persistent kernel, one CTA per SM, 128x128 output tiles handed out round-robin (n fastest, so CTAs that run
+// together share the A rows in L2 and the whole weight matrix stays L2-resident):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor 2D, 128B swizzle, 64-wide K slabs); the 4-stage ring keeps
+//                 running across tile boundaries, so loads for the next tile are in flight during the epilogue
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x128x16, kind::f16) into one of TWO
+//                 128-column accumulators, so the MMAs of tile i+1 overlap the epilogue of tile i
+//   warps 2..9  : epilogue, two groups of 4 warps (one per TMEM lane quarter), each group owns 64 columns:
+//                 tcgen05.ld 32 lanes x 32 columns -> +bias / exact-erf GELU -> fp32 staging chunk in smem ->
+//                 row-contiguous (coalesced) global reads of the residual and writes of the result
+// Both operands are K-major, which is the native layout of activations [rows, features] and of torch Linear
+// weights [out, in]; no transposes anywhere.
 #include <math.h>
 
 #include "common.cuh"
 
 namespace dss {
 
-constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16, STAGES = 3;
+constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16, STAGES = 4;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int B_TILE_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-constexpr int GEMM_THREADS = 192;
-constexpr int TMEM_COLS = 128;
-// ring + 1024 B alignment slack + barriers/bias
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int TMEM_COLS = 2 * BN;        // two fp32 accumulators
+constexpr int STG_LD = 36;               // staging chunk: 128 rows x 32 cols fp32, row pitch 36 (conflict-free)
+constexpr int STG_BYTES = BM * STG_LD * 4;
+// ring | 2 groups x 2 staging buffers | barriers | alignment slack
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + 256 + 1024;
+
+// Internal epilogue id (not part of the public enum): batched patch-affinity tile, see affinity.cu
+constexpr int EPI_AFFINITY_F32 = 100;
 
 struct EpiParams {
   void* out;
@@ -28,6 +38,14 @@ struct EpiParams {
   const float* aux;
   int ldo;
   int rin, rout;
+  // batched mode (gridDim.z = images): operand rows of image z start at z * batch_rows
+  int batch_rows;
+  // affinity epilogue
+  const unsigned int* img_max;  // [images] float bits of max(W) per image
+  const uint8_t* counts;        // [images, M, M] colour-KNN counts or null
+  float lambda;
+  int threshold;
+  int perm_blocks;              // B operand K-slab permutation for the split-fp16 Gram product (0 = none)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -46,66 +64,89 @@ __device__ __forceinline__ long long out_row(int m, const EpiParams& p) {
 }
 
 // Applies the epilogue to 32 consecutive columns [n, n+32) of one row and stores them.
-template <int EPI>
-__device__ __forceinline__ void epilogue_store(const float (&v)[32], int m, int n, const EpiParams& p) {
-  const long long r = out_row<EPI>(m, p);
-  if (r < 0) return;
-  if constexpr (EPI == DSS_EPI_BIAS_F16 || EPI == DSS_EPI_BIAS_GELU_F16) {
-    __half* o = reinterpret_cast<__half*>(p.out) + r * p.ldo + n;
+// ---- coalesced epilogue, second phase: one warp owns one output row of the tile at a time, lane l owns columns
+// n..n+3 (n = n0 + 4*l), so every global access of a warp is one contiguous 512 B (fp32) / 256 B (fp16) segment.
+__device__ __forceinline__ void store_row4_affinity(float4 v, int m, int n, int M, int z, const EpiParams& p) {
+  if (n >= p.ldo) return;
+  const float mx = __uint_as_float(p.img_max[z]);
+  const uint8_t* cnt = p.counts ? p.counts + ((long long)z * M + m) * M + n : nullptr;
+  float w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      float x[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) x[t] = (EPI == DSS_EPI_BIAS_GELU_F16) ? gelu_erf(v[j + t]) : v[j + t];
-      uint4 q;
-      q.x = pack_half2(x[0], x[1]);
-      q.y = pack_half2(x[2], x[3]);
-      q.z = pack_half2(x[4], x[5]);
-      q.w = pack_half2(x[6], x[7]);
-      *reinterpret_cast<uint4*>(o + j) = q;
-    }
-  } else {
-    float* o = reinterpret_cast<float*>(p.out) + r * p.ldo + n;
-    const float* aux = nullptr;
-    if constexpr (EPI == DSS_EPI_PATCH_F32) aux = p.aux + (long long)((m % p.rin) + 1) * p.ldo + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      if constexpr (EPI == DSS_EPI_BIAS_RESID_F32) {
-        const float4 y = *reinterpret_cast<const float4*>(o + j);
-        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
-      }
-      if constexpr (EPI == DSS_EPI_PATCH_F32) {
-        const float4 y = __ldg(reinterpret_cast<const float4*>(aux + j));
-        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
-      }
-      *reinterpret_cast<float4*>(o + j) = x;
-    }
+  for (int t = 0; t < 4; ++t) {
+    float x = w[t];
+    if (p.threshold) x = x > 0.f ? x : 0.f;   // W * (W > 0)
+    x = x / mx;                               // W / W.max()
+    if (cnt && n + t < M) x += static_cast<float>(cnt[t]) * p.lambda;   // + W_color * lambda
+    w[t] = (n + t < M) ? x : 0.f;             // row-pitch padding columns are zeros
   }
+  float* o = reinterpret_cast<float*>(p.out) + ((long long)z * M + m) * p.ldo + n;
+  *reinterpret_cast<float4*>(o) = make_float4(w[0], w[1], w[2], w[3]);
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__device__ __forceinline__ void store_row4(float4 v, int m, int n, const EpiParams& p) {
+  const long long r = out_row<EPI>(m, p);
+  if (r < 0) return;
+  if constexpr (EPI == DSS_EPI_BIAS_F16 || EPI == DSS_EPI_BIAS_GELU_F16) {
+    uint2 q;
+    q.x = pack_half2(v.x, v.y);
+    q.y = pack_half2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + r * p.ldo + n) = q;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ldo + n) = v;
+  }
+}
+
+// ---- one thread = one row x 32 columns (used by the CUDA-core checker kernel only)
+template <int EPI>
+__device__ __forceinline__ void epilogue_store(const float (&v)[32], int m, int n, const EpiParams& p) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    if constexpr (EPI == DSS_EPI_BIAS_GELU_F16) {
+      x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+    }
+    if constexpr (EPI == DSS_EPI_BIAS_RESID_F32) {
+      const float4 y = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + (long long)m * p.ldo + n + j);
+      x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    }
+    if constexpr (EPI == DSS_EPI_PATCH_F32) {
+      const float4 y = __ldg(reinterpret_cast<const float4*>(p.aux + (long long)((m % p.rin) + 1) * p.ldo + n + j));
+      x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    }
+    store_row4<EPI>(x, m, n + j, p);
+  }
+}
+
+struct TileCoord { int m0, n0, z; };
+__device__ __forceinline__ TileCoord decode_tile(int t, int tiles_m, int tiles_n) {
+  const int per_img = tiles_m * tiles_n;
+  const int z = t / per_img, rem = t - z * per_img;
+  return TileCoord{(rem / tiles_n) * BM, (rem % tiles_n) * BN, z};
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
-                        int N, int K, EpiParams p) {
+                        int N, int K, int tiles_m, int tiles_n, int total_tiles, EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment (the swizzle pattern is a function of address bits [7,10))
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
-  // barrier block layout: full[STAGES] | empty[STAGES] | tmem_full | tmem_ptr(u32) ... bias[128] at +128
+  float* stage_base = reinterpret_cast<float*>(gbase + STAGES * STAGE_BYTES);
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES + 4 * STG_BYTES;
+  // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr(u32)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 1);
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gbase + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
-  float* bias_s = reinterpret_cast<float*>(gbase + STAGES * STAGE_BYTES + 128);
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 2 + i); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(gbase + STAGES * STAGE_BYTES + 4 * STG_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
   const int num_kb = (K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -115,16 +156,15 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), EPI_WARPS);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr_addr, TMEM_COLS);
     tmem_relinquish();
-  }
-  if (warp >= 2) {
-    const int t = threadIdx.x - 64;  // 0..127
-    bias_s[t] = (n0 + t < N) ? __ldg(p.bias + n0 + t) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -133,54 +173,129 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
-        const uint32_t sa = base + s * STAGE_BYTES;
-        tma_load_2d(sa, &tmA, full_bar(s), kb * BK, m0);
-        tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kb * BK, n0);
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(t, tiles_m, tiles_n);
+        const int row_base = tc.z * p.batch_rows;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+          const uint32_t sa = base + s * STAGE_BYTES;
+          // split-fp16 Gram product: A = [hi | hi/64 | 64 lo], B = [hi | 64 lo | hi/64] are the same array read
+          // with the last two groups of K slabs swapped
+          int kbB = kb;
+          if (p.perm_blocks > 0 && kb >= p.perm_blocks)
+            kbB = kb < 2 * p.perm_blocks ? kb + p.perm_blocks : kb - p.perm_blocks;
+          tma_load_2d(sa, &tmA, full_bar(s), kb * BK, row_base + tc.m0);
+          tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kbB * BK, row_base + tc.n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(tempty_bar(buf), aph ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = base + s * STAGE_BYTES;
-        const uint32_t sb = sa + A_TILE_BYTES;
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advancing K inside the 128 B swizzle atom = advancing the start address by k*16 elements*2 B
-          const uint64_t adesc = umma_desc_sw128(sa + k * UMMA_K * 2);
-          const uint64_t bdesc = umma_desc_sw128(sb + k * UMMA_K * 2);
-          umma_f16_ss(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advancing K inside the 128 B swizzle atom = advancing the start address by k*16 elements*2 B
+            const uint64_t adesc = umma_desc_sw128(sa + k * UMMA_K * 2);
+            const uint64_t bdesc = umma_desc_sw128(sb + k * UMMA_K * 2);
+            umma_f16_ss(acc, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // smem slot is free once these MMAs have consumed it
         }
-        umma_commit(empty_bar(s));  // smem slot is free once these MMAs have consumed it
+        umma_commit(tfull_bar(buf));  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // epilogue warps 2..5: a warp may only touch TMEM lanes [32*(warp%4), +32)
+    // epilogue: group g owns columns [64g, 64g+64) of the tile; a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int ew = warp - 2;
+    const int g = ew >> 2, wq = ew & 3;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int m = m0 + row;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const TileCoord tc = decode_tile(t, tiles_m, tiles_n);
+      const int buf = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      mbar_wait(tfull_bar(buf), aph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      if (m < M && n0 + c * 32 < N) {
-        float v[32];
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = g * 64 + c * 32;      // first column of this chunk inside the tile
+        float* stg = stage_base + (g * 2 + c) * (STG_BYTES / 4);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + col0, r);
+        tmem_ld_wait();
+        if (c == 1) {  // this warp has read all of its TMEM: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        const int nc = tc.n0 + col0;           // global column of the chunk
+        // Phase 1: +bias (-> GELU) -> staging chunk (thread = row; pitch 36 floats -> conflict-free float4 writes)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c * 32 + j];
-        epilogue_store<EPI>(v, m, n0 + c * 32, p);
+        for (int j = 0; j < 32; j += 4) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && nc < N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + j));
+          float4 v;
+          v.x = __uint_as_float(r[j + 0]) + bv.x;
+          v.y = __uint_as_float(r[j + 1]) + bv.y;
+          v.z = __uint_as_float(r[j + 2]) + bv.z;
+          v.w = __uint_as_float(r[j + 3]) + bv.w;
+          if constexpr (EPI == DSS_EPI_BIAS_GELU_F16) {
+            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+          }
+          *reinterpret_cast<float4*>(stg + row * STG_LD + j) = v;
+        }
+        // group-local barrier (ids 1, 2). Double-buffered staging: one barrier per chunk is enough, because a
+        // thread reaches the barrier of chunk c only after finishing phase 2 of the previous user of buffer c^1.
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        // Phase 2: 8 lanes x 16 B cover the 128 B of one row of the chunk, 4 rows per warp instruction
+        if (nc < N) {
+          const int cl = (lane & 7) * 4;
+          float4 v[8], y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = wq * 32 + i * 4 + (lane >> 3);
+            const int m = tc.m0 + rr;
+            v[i] = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cl);
+            y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M) {
+              if constexpr (EPI == DSS_EPI_BIAS_RESID_F32)
+                y[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + (long long)m * p.ldo + nc + cl);
+              if constexpr (EPI == DSS_EPI_PATCH_F32)
+                y[i] = __ldg(reinterpret_cast<const float4*>(p.aux + (long long)((m % p.rin) + 1) * p.ldo + nc + cl));
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = wq * 32 + i * 4 + (lane >> 3);
+            const int m = tc.m0 + rr;
+            if (m >= M) continue;
+            float4 x = v[i];
+            x.x += y[i].x; x.y += y[i].y; x.z += y[i].z; x.w += y[i].w;
+            if constexpr (EPI == EPI_AFFINITY_F32)
+              store_row4_affinity(x, m, nc + cl, M, tc.z, p);
+            else
+              store_row4<EPI>(x, m, nc + cl, p);
+          }
+        }
       }
     }
   }
@@ -253,16 +368,20 @@ int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols) {
 
 template <int EPI>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& p,
-                     cudaStream_t st, int kclass) {
+                     cudaStream_t st, int kclass, int batch = 1) {
   static bool attr_set = false;
   if (!attr_set) {
     DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         GEMM_SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(cdiv(N, BN), cdiv(M, BM));
+  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, BN);
+  const int total = tiles_m * tiles_n * batch;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int grid = total < sms ? total : sms;
   LaunchScope scope(st, kclass);
-  gemm_f16_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, p);
+  gemm_f16_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, total, p);
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
 }
@@ -284,7 +403,7 @@ int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
                 int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass) {
   int rc = check_gemm_args(M, N, K, epi, bias, out, aux, rin, rout);
   if (rc) return rc;
-  EpiParams p{out, bias, aux, N, rin, rout};
+  EpiParams p{out, bias, aux, N, rin, rout, 0, nullptr, nullptr, 0.f, 0, 0};
   switch (epi) {
     case DSS_EPI_BIAS_F16: return launch_tc<DSS_EPI_BIAS_F16>(tmA, tmB, M, N, K, p, st, kclass);
     case DSS_EPI_BIAS_GELU_F16: return launch_tc<DSS_EPI_BIAS_GELU_F16>(tmA, tmB, M, N, K, p, st, kclass);
@@ -295,6 +414,16 @@ int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
   }
   set_error("gemm: unknown epilogue %d", epi);
   return DSS_ERR_BAD_ARG;
+}
+
+// Batched Gram product for the affinity build: per image z, W[z] = epilogue(S[z] S'[z]^T) with S = split-fp16 rows
+// [images*Nimg, 3d] (see affinity.cu). N output columns cover the padded pitch ldw.
+int affinity_gemm_tc(const CUtensorMap& tmS, int images, int Nimg, int d, float* Wout, int ldw,
+                     const unsigned int* img_max, const uint8_t* counts, float lambda, int threshold,
+                     cudaStream_t st) {
+  EpiParams p{Wout, nullptr, nullptr, ldw, 0, 0, Nimg, img_max, counts, lambda, threshold, d / BK};
+  DSS_REQUIRE(d % BK == 0, "affinity: feature dim must be a multiple of %d for the tensor-core path (got %d)", BK, d);
+  return launch_tc<EPI_AFFINITY_F32>(tmS, tmS, Nimg, ldw, 3 * d, p, st, KC_AFFINITY, images);
 }
 
 template <int EPI>
@@ -329,7 +458,7 @@ extern "C" int dss_op_gemm_f16_simt(const void* A, const void* Wt, const float* 
   int rc = check_gemm_args(M, N, K, epilogue, bias, out, aux, rin, rout);
   if (rc) return rc;
   DSS_REQUIRE(A && Wt, "gemm: null operand");
-  EpiParams p{out, bias, aux, N, rin, rout};
+  EpiParams p{out, bias, aux, N, rin, rout, 0, nullptr, nullptr, 0.f, 0, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epilogue) {
     case DSS_EPI_BIAS_F16: return launch_simt<DSS_EPI_BIAS_F16>(A, Wt, M, N, K, p, st);

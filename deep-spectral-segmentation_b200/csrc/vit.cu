@@ -2,7 +2,7 @@
 // Replaces utils.get_model + model.get_intermediate_layers + the qkv forward hook of the reference
 // (extract/extract_utils.py:40-50, extract/extract.py:49-53,82-98).
 //
-// Per block:  LN1 -> [tcgen05 GEMM] qkv (f16) -> flash attention -> [tcgen05 GEMM + residual] proj
+// Per block:  LN1 -> [tcgen05 GEMM] qkv (f16) -> tcgen05 flash attention -> [tcgen05 GEMM + residual] proj
 //             LN2 -> [tcgen05 GEMM + GELU] fc1 (f16) -> [tcgen05 GEMM + residual] fc2
 // The residual stream stays fp32; GEMM operands are fp16 (11-bit significand, same as TF32), accumulation fp32.
 // The block the reference hooks is pruned to LN1 + the K third of its qkv projection, CLS row dropped in the
@@ -24,7 +24,7 @@ int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
 int launch_im2col(const uint8_t* img, void* patches, int B, int H, int W, int P, cudaStream_t st);
 int launch_cls_row(float* x, const float* cls, const float* pos, int B, int T, int d, cudaStream_t st);
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int M, int d, float eps, cudaStream_t st);
-int launch_attention(const void* qkv, void* out, int B, int T, int heads, cudaStream_t st);
+int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cudaStream_t st);
 
 __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,7 +195,7 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
     if ((rc = gemm_f16_tc(tm_xn, bw.tm_qkv, bw.qkv_b, w.qkv, M, 3 * d, d, DSS_EPI_BIAS_F16, nullptr, 0, 0, st,
                           KC_GEMM_QKV)))
       return rc;
-    if ((rc = launch_attention(w.qkv, w.attn, B, T, c.heads, st))) return rc;
+    if ((rc = launch_attention_tc(w.qkv, w.attn, B, T, c.heads, st))) return rc;
     if ((rc = gemm_f16_tc(tm_attn, bw.tm_proj, bw.proj_b, w.x, M, d, d, DSS_EPI_BIAS_RESID_F32, nullptr, 0, 0, st,
                           KC_GEMM_PROJ)))
       return rc;

@@ -132,6 +132,8 @@ int dss_op_layernorm_f16(const float* x, const float* gamma, const float* beta, 
                          dss_stream_t stream);
 /* qkv f16 [B, T, 3*d] (q | k | v, heads of 64 inside each) -> out f16 [B, T, d] = softmax(q k^T / 8) v */
 int dss_op_attention_f16(const void* qkv, void* out, int B, int T, int heads, dss_stream_t stream);
+/* same contract on tcgen05 (TMA-fed QK^T and PV UMMAs, S and O in TMEM); the ViT forward uses this one */
+int dss_op_attention_tc_f16(const void* qkv, void* out, int B, int T, int heads, dss_stream_t stream);
 /* images_u8 [B,H,W,3] -> patches f16 [B*N, 3*P*P], column order (c, py, px), normalised */
 int dss_op_im2col_f16(const uint8_t* images_u8, void* patches, int B, int H, int W, int P, dss_stream_t stream);
 

@@ -96,21 +96,22 @@ def test_layernorm(cuda, d):
     assert err <= 1e-3 * ref.abs().max().item() + 1e-3, err   # fp16 output rounding only
 
 
-@pytest.mark.parametrize("B,T,heads", [(1, 64, 6), (2, 197, 6), (2, 901, 6), (1, 130, 12)])
-def test_attention(cuda, B, T, heads):
+@pytest.mark.parametrize("impl", ["dss_op_attention_tc_f16", "dss_op_attention_f16"])
+@pytest.mark.parametrize("B,T,heads", [(1, 64, 6), (2, 197, 6), (2, 901, 6), (1, 130, 12), (3, 257, 6)])
+def test_attention(cuda, B, T, heads, impl):
     _lib = load_pkg("_lib"); lib = _lib.load()
     g = torch.Generator(device="cuda").manual_seed(T)
     d = heads * 64
     qkv = (torch.randn(B, T, 3 * d, device=cuda, generator=g) * 1.5).half()
     out = torch.full((B, T, d), float("nan"), device=cuda, dtype=torch.float16)
-    _lib.check(lib.dss_op_attention_f16(qkv.data_ptr(), out.data_ptr(), B, T, heads, _lib.stream_ptr()))
+    _lib.check(getattr(lib, impl)(qkv.data_ptr(), out.data_ptr(), B, T, heads, _lib.stream_ptr()))
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     att = ((q @ k.transpose(-2, -1)) * 0.125).softmax(-1)
     ref = (att @ v).transpose(1, 2).reshape(B, T, d)
     assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()
-    print(f"attention B={B} T={T}: max err {err:.3e} (ref max {ref.abs().max().item():.3f})")
+    print(f"{impl} B={B} T={T}: max err {err:.3e} (ref max {ref.abs().max().item():.3f})")
     assert err <= 4e-3 * max(1.0, ref.abs().max().item()), err  # P and output rounded to fp16
 
 
