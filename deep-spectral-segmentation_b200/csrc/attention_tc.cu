@@ -9,7 +9,7 @@
 //   warps 2..5  softmax / accumulate: thread = query row (tcgen05.ld 32x32b), running max / sum in base 2,
 //               P_j written as fp16 into the K-major 128 B-swizzled smem tile the PV MMA reads, and the output
 //               accumulated in REGISTERS: O = O * 2^(m_old - m_new) + O_j, so TMEM is never rescaled in place.
-// Two CTAs are resident per SM (112 KB smem, 256 TMEM columns each): while one CTA's softmax warps are busy
+// Two CTAs are resident per SM (96 KB smem, 256 TMEM columns each): while one CTA's softmax warps are busy
 // (MUFU-bound: 128x128 exp2 per tile) the other CTA's MMAs run.
 #include <math.h>
 
@@ -21,7 +21,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols);
 
 constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64, FA_THREADS = 192;
 constexpr int FA_TILE = FA_BM * FA_D * 2;             // 16 KB: one [128 x 64] fp16 tile
-constexpr int FA_SMEM = FA_TILE * (1 + 2 + 2) + 2 * FA_TILE;  // Q | K0 K1 | V0 V1 | P(128x128) = 112 KB
+constexpr int FA_SMEM = FA_TILE * (1 + 2 + 2 + 1);  // Q | K0 K1 | V0 V1 | P(keys 64..127) = 96 KB; P(keys 0..63) reuses K_j
 constexpr int FA_TMEM_COLS = 256;
 constexpr int FA_S_COL = 0, FA_O_COL = 128;
 
@@ -33,7 +33,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
 
   const uint32_t base = smem_u32(fa_smem);
   if ((base & 1023u) != 0) __trap();  // the 128 B swizzle pattern is a function of address bits [7,10)
-  const uint32_t sQ = base, sK = base + FA_TILE, sV = base + 3 * FA_TILE, sP = base + 5 * FA_TILE;
+  // P_j (128 queries x 128 keys fp16 = two 64-key atoms): atom 0 overwrites K_j, which is dead once S_j = Q K_j^T has
+  // completed (s_full) and is not refilled before PV_j has completed (kv_empty); atom 1 has its own buffer.
+  const uint32_t sQ = base, sK = base + FA_TILE, sV = base + 3 * FA_TILE, sP1 = base + 5 * FA_TILE;
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t q_full = bar0, s_full = bar0 + 40, p_full = bar0 + 48, o_full = bar0 + 56;
   auto kv_full = [&](int s) { return bar0 + 8u + 8u * s; };
@@ -101,7 +103,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k) {
-          const uint64_t adesc = umma_desc_sw128(sP + (k >> 2) * FA_TILE + (k & 3) * 32);   // 64-key atoms, K-major
+          const uint32_t patom = (k >> 2) ? sP1 : sK + s * FA_TILE;                        // 64-key atoms, K-major
+          const uint64_t adesc = umma_desc_sw128(patom + (k & 3) * 32);
           const uint64_t bdesc = umma_desc_sw128(sV + s * FA_TILE + k * 16 * 128);          // 16 key rows per step
           umma_f16_ss(tmem_base + FA_O_COL, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
         }
@@ -118,28 +121,36 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
     float o[FA_D];
 #pragma unroll
     for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
-    const uint32_t prow = sP + r * 128;   // this row inside each 64-key atom of P
     for (int j = 0; j < nt; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int nvalid = T - j * FA_BN;   // keys of this tile that exist (>= 128 except for the last tile)
-      // pass 1: row maximum
+      const bool full_tile = nvalid >= FA_BN;
+      const uint32_t prow0 = sK + (j & 1) * FA_TILE + r * 128;   // this row inside P atom 0 (keys 0..63)
+      const uint32_t prow1 = sP1 + r * 128;                      // ... and atom 1 (keys 64..127)
+      // pass 1: row maximum (two 32-column TMEM loads in flight per wait)
       float mx = m_run;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + FA_S_COL + c * 32, v);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(lane_addr + FA_S_COL + c * 32, v0);
+        tmem_ld_32x32(lane_addr + FA_S_COL + c * 32 + 32, v1);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = (c * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY;
-          mx = fmaxf(mx, x);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v0[i]));
+            if (c * 32 + 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v1[i]));
+          }
         }
       }
       const float corr = exp2f((m_run - mx) * sc);   // first tile: exp2(-inf) = 0
       const float msc = mx * sc;
       m_run = mx;
-      // pass 2: P = 2^(s*c - m*c), row sum, fp16 P into the swizzled K-major tile
+      // pass 2: P = 2^(s*c - m*c), row sum, fp16 P into the swizzled K-major tiles
       float rs = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -147,18 +158,29 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
         tmem_ld_32x32(lane_addr + FA_S_COL + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = (c * 32 + i < nvalid) ? exp2f(fmaf(__uint_as_float(v[i]), sc, -msc)) : 0.f;
-          const float p1 = (c * 32 + i + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sc, -msc)) : 0.f;
-          rs += p0 + p1;
-          pk[i >> 1] = pack_half2(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = exp2f(fmaf(__uint_as_float(v[i]), sc, -msc));
+            const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), sc, -msc));
+            rs += p0 + p1;
+            pk[i >> 1] = pack_half2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c * 32 + i < nvalid) ? exp2f(fmaf(__uint_as_float(v[i]), sc, -msc)) : 0.f;
+            const float p1 = (c * 32 + i + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sc, -msc)) : 0.f;
+            rs += p0 + p1;
+            pk[i >> 1] = pack_half2(p0, p1);
+          }
         }
         // keys [32c, 32c+32) = 4 chunks of 8 keys; chunk g of the row: atom g/8, slot (g%8) ^ (r%8)
+        const uint32_t prow = (c < 2) ? prow0 : prow1;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int g = c * 4 + t;
-          const uint32_t addr = prow + (g >> 3) * FA_TILE + ((((g & 7) ^ (r & 7))) << 4);
+          const int g = (c & 1) * 4 + t;
+          const uint32_t addr = prow + (((g ^ (r & 7))) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[t * 4 + 0]), "r"(pk[t * 4 + 1]),
                        "r"(pk[t * 4 + 2]), "r"(pk[t * 4 + 3])
                        : "memory");
@@ -171,19 +193,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
       // O = O * corr + P_j V_j
       mbar_wait(o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + FA_O_COL + c * 32, v);
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(lane_addr + FA_O_COL, v0);
+        tmem_ld_32x32(lane_addr + FA_O_COL + 32, v1);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], corr, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) {
+          o[i] = fmaf(o[i], corr, __uint_as_float(v0[i]));
+          o[32 + i] = fmaf(o[32 + i], corr, __uint_as_float(v1[i]));
+        }
       }
       tc_fence_before();          // O_j consumed before PV_{j+1} may overwrite it (ordered via p_full(j+1))
     }
     // epilogue: normalise, stage the [128 x 64] fp16 tile in the (now idle) P buffer, store coalesced
     const float inv = 1.0f / l_run;
-    uint8_t* stage = fa_smem + 5 * FA_TILE;   // rows of 128 B + 16 B pad -> conflict-free row-per-thread writes
+    uint8_t* stage = fa_smem + FA_TILE;       // K/V ring is idle now; rows of 128 B + 16 B pad -> conflict-free writes
 #pragma unroll
     for (int i = 0; i < FA_D; i += 8) {
       uint4 w;
