@@ -13,7 +13,7 @@
 
 namespace dss {
 
-int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols);
+int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
 int affinity_gemm_tc(const CUtensorMap& tmS, int images, int Nimg, int d, float* Wout, int ldw,
                      const unsigned int* img_max, const uint8_t* counts, float lambda, int threshold, cudaStream_t st);
 
@@ -66,6 +66,41 @@ rownorm_split_kernel(const float* __restrict__ f, __half* __restrict__ S, unsign
   if (lane == 0) atomicMax(img_max + row / N, __float_as_uint(fmaxf(s2, 0.f)));
 }
 
+// F.normalize(p=2, dim=-1): one warp per row
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const float* __restrict__ f, float* __restrict__ out, int rows, int d) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = f + (long long)row * d;
+  float ss = 0.f;
+  for (int k = lane; k < d; k += 32) ss = fmaf(x[k], x[k], ss);
+  const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  for (int k = lane; k < d; k += 32) out[(long long)row * d + k] = x[k] / denom;
+}
+
+// F.interpolate(mode='bilinear', align_corners=False) on a [Hp, Wp] grid of d-channel features stored [N, d]
+__global__ void __launch_bounds__(256)
+upsample_bilinear_kernel(const float* __restrict__ f, float* __restrict__ out, int Hp, int Wp, int d, int Hl, int Wl) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x;  // output pixel
+  const int oy = pix / Wl, ox = pix % Wl;
+  const float sy = fmaxf(((float)oy + 0.5f) * ((float)Hp / (float)Hl) - 0.5f, 0.f);
+  const float sx = fmaxf(((float)ox + 0.5f) * ((float)Wp / (float)Wl) - 0.5f, 0.f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < Hp - 1 ? 1 : 0), x1 = x0 + (x0 < Wp - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float* base = f + (long long)b * Hp * Wp * d;
+  const float* p00 = base + (long long)(y0 * Wp + x0) * d;
+  const float* p01 = base + (long long)(y0 * Wp + x1) * d;
+  const float* p10 = base + (long long)(y1 * Wp + x0) * d;
+  const float* p11 = base + (long long)(y1 * Wp + x1) * d;
+  float* o = out + ((long long)b * Hl * Wl + pix) * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    o[c] = hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]);
+}
+
 static size_t split_bytes(int B, int N, int d) {
   const int dpad = (d + 63) / 64 * 64;
   return align_up((size_t)B * N * 3 * dpad * sizeof(__half) + 128 * 3 * dpad * sizeof(__half), 1024);  // + tile overrun
@@ -110,8 +145,28 @@ extern "C" int dss_affinity(const float* feats, int B, int N, int d, int flags, 
     DSS_CHECK_CUDA(cudaGetLastError());
   }
   CUtensorMap tmS;
-  int rc = make_tmap_f16(&tmS, S, rows, 3 * dpad);
+  int rc = make_tmap_f16(&tmS, S, rows, 3 * dpad, 128);
   if (rc) return rc;
   return affinity_gemm_tc(tmS, B, N, dpad, Wmat, ldw, img_max, color_counts, color_lambda,
-                          (flags & DSS_AFF_THRESHOLD_AT_ZERO) ? 1 : 0, st);
+                          ((flags & DSS_AFF_THRESHOLD_AT_ZERO) ? 1 : 0) | ((flags & DSS_AFF_NO_MAX_SCALE) ? 2 : 0), st);
+}
+
+extern "C" int dss_normalize_rows(const float* feats, int rows, int d, float* out, dss_stream_t stream) {
+  DSS_REQUIRE(feats && out && rows > 0 && d > 0, "normalize_rows: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchScope scope(st, KC_ROWNORM);
+  normalize_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(feats, out, rows, d);
+  DSS_CHECK_CUDA(cudaGetLastError());
+  return DSS_OK;
+}
+
+extern "C" int dss_upsample_bilinear(const float* feats, int B, int Hp, int Wp, int d, int Hl, int Wl, float* out,
+                                     dss_stream_t stream) {
+  DSS_REQUIRE(feats && out, "upsample: null pointer");
+  DSS_REQUIRE(B > 0 && Hp > 0 && Wp > 0 && d > 0 && Hl > 0 && Wl > 0, "upsample: empty problem");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchScope scope(st, KC_MISC);
+  upsample_bilinear_kernel<<<dim3(Hl * Wl, B), 128, 0, st>>>(feats, out, Hp, Wp, d, Hl, Wl);
+  DSS_CHECK_CUDA(cudaGetLastError());
+  return DSS_OK;
 }

@@ -17,7 +17,7 @@
 
 namespace dss {
 
-int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols);
+int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
 
 constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64, FA_THREADS = 192;
 constexpr int FA_TILE = FA_BM * FA_D * 2;             // 16 KB: one [128 x 64] fp16 tile
@@ -244,7 +244,7 @@ int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cud
     attr_set = true;
   }
   CUtensorMap tm;
-  int rc = make_tmap_f16(&tm, qkv, B * T, 3 * heads * FA_D);
+  int rc = make_tmap_f16(&tm, qkv, B * T, 3 * heads * FA_D, FA_BM);
   if (rc) return rc;
   dim3 grid(cdiv(T, FA_BM), heads, B);
   LaunchScope scope(st, KC_ATTENTION);

@@ -30,7 +30,8 @@ struct EigParams {
   float* resid;       // [B, K] or null
   float* basis;       // per-CTA scratch: [(mmax+1), Npad]
   double* tri;        // per-CTA scratch: [2, Kw, mmax]   (Ritz vectors of T, temp)
-  int B, N, ldw, Npad, K, mmax, lapnorm;
+  int B, N, ldw, Npad, K, mmax;
+  int mode;           // 0: normalised Laplacian pencil, 1: unnormalised Laplacian, 2: plain top-K of the matrix itself
   float tol;
 };
 
@@ -89,7 +90,10 @@ __host__ __device__ inline size_t eig_double_bytes(int mmax) {
 __global__ void __launch_bounds__(EIG_THREADS, 2)
 lanczos_laplacian_kernel(EigParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int N = p.N, Npad = p.Npad, mmax = p.mmax, K = p.K, Kw = p.K - 1, ldw = p.ldw;
+  const int N = p.N, Npad = p.Npad, mmax = p.mmax, K = p.K, ldw = p.ldw;
+  const bool lapn = p.mode == 0, plain = p.mode == 2;
+  const int Kw = plain ? p.K : p.K - 1;   // Ritz pairs wanted from Lanczos (the Laplacian's null vector is analytic)
+  const int off = plain ? 0 : 1;          // output slot of the first Lanczos pair
   // shared layout
   double* alpha = reinterpret_cast<double*>(smem_raw);      // [mmax]
   double* beta = alpha + mmax;                               // [mmax]   beta[j] = ||w_j|| (couples j, j+1)
@@ -141,9 +145,12 @@ lanczos_laplacian_kernel(EigParams p) {
     for (int i = tid; i < Npad; i += EIG_THREADS) {
       const float dg = wv[i];
       if (i < N) {
-        if (p.lapnorm) {
+        if (lapn) {
           dsc[i] = (float)(1.0 / sqrt((double)dg));
           u0[i] = (float)(sqrt((double)dg) / sqrt(sumD));
+        } else if (plain) {
+          dsc[i] = 1.0f;   // operator = the matrix itself, nothing is deflated
+          u0[i] = 0.f;
         } else {
           dsc[i] = dg;
           u0[i] = (float)(1.0 / sqrt((double)N));
@@ -158,6 +165,7 @@ lanczos_laplacian_kernel(EigParams p) {
 
     int n = 0;          // Lanczos steps done
     int converged = (Kw <= 0);
+    bool have_theta = false;
     if (Kw > 0) {
       // ---- start vector: deterministic pseudo-random, orthogonal to u0
       for (int i = tid; i < Npad; i += EIG_THREADS) wv[i] = (i < N) ? hash_uniform((uint32_t)i, 0x1234567u) : 0.f;
@@ -184,7 +192,7 @@ lanczos_laplacian_kernel(EigParams p) {
       double anorm = 1.0;
       for (int j = 0; j < mmax; ++j) {
         // ---- mat-vec  w = S v  (lapnorm)   or   w = (W - D) v  (unnormalised: top of -(D-W))
-        for (int i = tid; i < Npad; i += EIG_THREADS) xs[i] = p.lapnorm ? dsc[i] * vcur[i] : vcur[i];
+        for (int i = tid; i < Npad; i += EIG_THREADS) xs[i] = lapn ? dsc[i] * vcur[i] : vcur[i];
         __syncthreads();
         for (int r = warp * 2; r < N; r += EIG_WARPS * 2) {
           const bool two = (r + 1) < N;
@@ -201,8 +209,8 @@ lanczos_laplacian_kernel(EigParams p) {
           }
           const float sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
           if (lane == 0) {
-            wv[r] = p.lapnorm ? dsc[r] * sa : sa - dsc[r] * xs[r];
-            if (two) wv[r + 1] = p.lapnorm ? dsc[r + 1] * sb : sb - dsc[r + 1] * xs[r + 1];
+            wv[r] = lapn ? dsc[r] * sa : (plain ? sa : sa - dsc[r] * xs[r]);
+            if (two) wv[r + 1] = lapn ? dsc[r + 1] * sb : (plain ? sb : sb - dsc[r + 1] * xs[r + 1]);
           }
         }
         __syncthreads();
@@ -346,32 +354,42 @@ lanczos_laplacian_kernel(EigParams p) {
           }
           __syncthreads();
           converged = s_flag;
+          have_theta = true;
           if (converged || breakdown) break;
         }
       }
     }
 
+    // plain mode serves which='LM': report if a negative eigenvalue is larger in magnitude than the K-th positive one
+    int lm_differs = 0;
+    if (plain && n > 0 && have_theta) {
+      // number of Ritz values below -|theta_K|: any such eigenvalue would be selected by which='LM' instead
+      lm_differs = sturm_count(alpha, beta2, n, -fabs(theta[min(Kw, n) - 1])) > 0 ? 1 : 0;
+    }
     // ---- outputs: ascending eigenvalues, D-orthonormal (lapnorm) / unit (unnormalised) vectors, sign rule
     float* ev = p.evals + (size_t)img * K;
     float* evec = p.evecs + (size_t)img * K * N;
     {
-      const float c0 = p.lapnorm ? (float)(1.0 / sqrt(sumD)) : (float)(1.0 / sqrt((double)N));
-      for (int i = tid; i < N; i += EIG_THREADS) evec[i] = c0;
+      const float c0 = lapn ? (float)(1.0 / sqrt(sumD)) : (float)(1.0 / sqrt((double)N));
+      if (!plain)
+        for (int i = tid; i < N; i += EIG_THREADS) evec[i] = c0;
       if (tid == 0) {
-        ev[0] = 0.f;
-        if (p.resid) p.resid[(size_t)img * K] = 0.f;
+        if (!plain) {
+          ev[0] = 0.f;
+          if (p.resid) p.resid[(size_t)img * K] = 0.f;
+        }
         p.info[img * 4 + 0] = n;
         p.info[img * 4 + 1] = converged ? 1 : 0;
-        p.info[img * 4 + 2] = 0;
+        p.info[img * 4 + 2] = lm_differs;
         p.info[img * 4 + 3] = 0;
       }
     }
     const int have = min(Kw, n);  // Ritz pairs available
     for (int k = 0; k < Kw; ++k) {
-      float* out = evec + (size_t)(k + 1) * N;
+      float* out = evec + (size_t)(k + off) * N;
       if (k >= have) {  // degenerate request (K-1 > steps possible): fill with NaN
         for (int i = tid; i < N; i += EIG_THREADS) out[i] = __int_as_float(0x7fc00000);
-        if (tid == 0) ev[k + 1] = __int_as_float(0x7fc00000);
+        if (tid == 0) ev[k + off] = __int_as_float(0x7fc00000);
         continue;
       }
       const double* zs = triS + (size_t)k * mmax;
@@ -385,7 +403,7 @@ lanczos_laplacian_kernel(EigParams p) {
       const float inv = (float)(1.0 / sqrt(block_sum(d, red, tid)));
       int pos = 0;
       for (int i = tid; i < N; i += EIG_THREADS) {
-        const float v = p.lapnorm ? wv[i] * inv * dsc[i] : wv[i] * inv;
+        const float v = lapn ? wv[i] * inv * dsc[i] : wv[i] * inv;
         wv[i] = v;
         pos += v > 0.f;
       }
@@ -394,8 +412,8 @@ lanczos_laplacian_kernel(EigParams p) {
       const float sgn = (2 * npos > N && npos < N) ? -1.f : 1.f;
       for (int i = tid; i < N; i += EIG_THREADS) out[i] = sgn * wv[i];
       if (tid == 0) {
-        ev[k + 1] = p.lapnorm ? (float)(1.0 - theta[k]) : (float)(-theta[k]);
-        if (p.resid) p.resid[(size_t)img * K + k + 1] = (float)resid_s[k];
+        ev[k + off] = lapn ? (float)(1.0 - theta[k]) : (plain ? (float)theta[k] : (float)(-theta[k]));
+        if (p.resid) p.resid[(size_t)img * K + k + off] = (float)resid_s[k];
       }
       __syncthreads();
     }
@@ -434,13 +452,13 @@ extern "C" size_t dss_eigsh_workspace_bytes(int B, int N, int K, int max_steps) 
   const int mmax = eig_resolve(N, K, max_steps);
   const int grid = eig_grid(B, Npad, mmax);
   const size_t basis = align_up((size_t)grid * (mmax + 1) * Npad * sizeof(float), 256);
-  const size_t tri = align_up((size_t)grid * 2 * (K > 1 ? K - 1 : 1) * mmax * sizeof(double), 256);
+  const size_t tri = align_up((size_t)grid * 2 * K * mmax * sizeof(double), 256);
   return basis + tri;
 }
 
-extern "C" int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int K, int lapnorm, float tol,
-                                   int max_steps, float* evals, float* evecs, int* info, float* resid, void* ws,
-                                   size_t ws_bytes, dss_stream_t stream) {
+static int eigsh_launch(const float* Wmat, int ldw, int B, int N, int K, int mode, float tol, int max_steps,
+                        float* evals, float* evecs, int* info, float* resid, void* ws, size_t ws_bytes,
+                        dss_stream_t stream) {
   DSS_REQUIRE(Wmat && evals && evecs && info && ws, "eigsh: null pointer");
   DSS_REQUIRE(B > 0 && N > 1, "eigsh: empty problem B=%d N=%d", B, N);
   DSS_REQUIRE(K >= 1 && K <= EIG_MAX_K && K < N, "eigsh: need 1 <= K <= %d and K < N (K=%d N=%d)", EIG_MAX_K, K, N);
@@ -454,7 +472,7 @@ extern "C" int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int
   }
   EigParams p;
   p.W = Wmat; p.evals = evals; p.evecs = evecs; p.info = info; p.resid = resid;
-  p.B = B; p.N = N; p.ldw = ldw; p.Npad = (N + 3) & ~3; p.K = K; p.lapnorm = lapnorm ? 1 : 0;
+  p.B = B; p.N = N; p.ldw = ldw; p.Npad = (N + 3) & ~3; p.K = K; p.mode = mode;
   p.mmax = eig_resolve(N, K, max_steps);
   p.tol = tol > 0.f ? tol : 1e-6f;
   const int grid = eig_grid(B, p.Npad, p.mmax);
@@ -471,4 +489,15 @@ extern "C" int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int
   lanczos_laplacian_kernel<<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
+}
+
+extern "C" int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int K, int lapnorm, float tol,
+                                   int max_steps, float* evals, float* evecs, int* info, float* resid, void* ws,
+                                   size_t ws_bytes, dss_stream_t stream) {
+  return eigsh_launch(Wmat, ldw, B, N, K, lapnorm ? 0 : 1, tol, max_steps, evals, evecs, info, resid, ws, ws_bytes, stream);
+}
+
+extern "C" int dss_eigsh_topk(const float* Amat, int lda, int B, int N, int K, float tol, int max_steps, float* evals,
+                              float* evecs, int* info, float* resid, void* ws, size_t ws_bytes, dss_stream_t stream) {
+  return eigsh_launch(Amat, lda, B, N, K, 2, tol, max_steps, evals, evecs, info, resid, ws, ws_bytes, stream);
 }

@@ -17,17 +17,22 @@
 
 namespace dss {
 
-constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int B_TILE_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-constexpr int TMEM_COLS = 2 * BN;        // two fp32 accumulators
 constexpr int STG_LD = 36;               // staging chunk: 128 rows x 32 cols fp32, row pitch 36 (conflict-free)
 constexpr int STG_BYTES = BM * STG_LD * 4;
-// ring | 2 groups x 2 staging buffers | barriers | alignment slack
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + 256 + 1024;
+// Tile width BN in {128, 192, 256}: wider tiles re-read the A rows less often from L2 (the K = 384 GEMMs of
+// ViT-S are L2 -> SM bandwidth bound at 128 x 128: 192 KB of operands per 12.6 MFLOP tile).
+template <int BN> struct TileCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = BN == 128 ? 4 : 3;
+  static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;   // two fp32 accumulators, power-of-two allocation
+  // ring | 2 groups x 2 staging buffers | barriers | alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + 256 + 1024;
+};
 
 // Internal epilogue id (not part of the public enum): batched patch-affinity tile, see affinity.cu
 constexpr int EPI_AFFINITY_F32 = 100;
@@ -44,11 +49,25 @@ struct EpiParams {
   const unsigned int* img_max;  // [images] float bits of max(W) per image
   const uint8_t* counts;        // [images, M, M] colour-KNN counts or null
   float lambda;
-  int threshold;
+  int threshold;                // bit 0: relu threshold, bit 1: do not divide by max(W)
   int perm_blocks;              // B operand K-slab permutation for the split-fp16 Gram product (0 = none)
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU x * Phi(x), branch-free. erfc via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, three orders of
+// magnitude below the fp16 rounding of the value this feeds): for z = |x|/sqrt(2),
+//   q = 0.5 * erfc(z) = 0.5 * t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + 0.3275911 z)
+// and Phi(x) = 1 - q for x >= 0, q for x < 0 (no cancellation on the negative side).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float q = 0.5f * t * poly * __expf(-z * z);
+  const float phi = x >= 0.f ? 1.0f - q : q;
+  return x * phi;
+}
 
 // Row of the output buffer that GEMM row m maps to (or -1: skip).
 template <int EPI>
@@ -74,8 +93,8 @@ __device__ __forceinline__ void store_row4_affinity(float4 v, int m, int n, int 
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     float x = w[t];
-    if (p.threshold) x = x > 0.f ? x : 0.f;   // W * (W > 0)
-    x = x / mx;                               // W / W.max()
+    if (p.threshold & 1) x = x > 0.f ? x : 0.f;   // W * (W > 0)
+    if (!(p.threshold & 2)) x = x / mx;           // W / W.max()   (skipped for which_matrix='affinity'/'affinity_svd')
     if (cnt && n + t < M) x += static_cast<float>(cnt[t]) * p.lambda;   // + W_color * lambda
     w[t] = (n + t < M) ? x : 0.f;             // row-pitch padding columns are zeros
   }
@@ -119,16 +138,19 @@ __device__ __forceinline__ void epilogue_store(const float (&v)[32], int m, int 
 }
 
 struct TileCoord { int m0, n0, z; };
+template <int BN>
 __device__ __forceinline__ TileCoord decode_tile(int t, int tiles_m, int tiles_n) {
   const int per_img = tiles_m * tiles_n;
   const int z = t / per_img, rem = t - z * per_img;
   return TileCoord{(rem / tiles_n) * BM, (rem % tiles_n) * BN, z};
 }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
                         int N, int K, int tiles_m, int tiles_n, int total_tiles, EpiParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, TMEM_COLS = Cfg::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment (the swizzle pattern is a function of address bits [7,10))
   const uint32_t raw = smem_u32(smem_raw);
@@ -175,7 +197,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     if (lane == 0) {
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(t, tiles_m, tiles_n);
+        const TileCoord tc = decode_tile<BN>(t, tiles_m, tiles_n);
         const int row_base = tc.z * p.batch_rows;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
@@ -189,7 +211,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (p.perm_blocks > 0 && kb >= p.perm_blocks)
             kbB = kb < 2 * p.perm_blocks ? kb + p.perm_blocks : kb - p.perm_blocks;
           tma_load_2d(sa, &tmA, full_bar(s), kb * BK, row_base + tc.m0);
-          tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kbB * BK, row_base + tc.n0);
+          tma_load_2d(sa + A_TILE_BYTES, &tmB, full_bar(s), kbB * BK, row_base + tc.n0);  // box: 64 x BN rows
         }
       }
     }
@@ -223,26 +245,27 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
   } else {
-    // epilogue: group g owns columns [64g, 64g+64) of the tile; a warp may only touch TMEM lanes [32*(warp%4), +32)
+    // epilogue: group g owns columns [g*BN/2, (g+1)*BN/2) of the tile; a warp may only touch TMEM lanes [32*(warp%4), +32)
+    constexpr int NCHUNK = BN / 64;            // 32-column chunks per group
     const int ew = warp - 2;
     const int g = ew >> 2, wq = ew & 3;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    int lt = 0;
+    int lt = 0, cc = 0;  // cc: running chunk counter -> consecutive chunks always use alternate staging buffers
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      const TileCoord tc = decode_tile(t, tiles_m, tiles_n);
+      const TileCoord tc = decode_tile<BN>(t, tiles_m, tiles_n);
       const int buf = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       mbar_wait(tfull_bar(buf), aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int col0 = g * 64 + c * 32;      // first column of this chunk inside the tile
-        float* stg = stage_base + (g * 2 + c) * (STG_BYTES / 4);
+      for (int c = 0; c < NCHUNK; ++c, ++cc) {
+        const int col0 = g * (BN / 2) + c * 32;  // first column of this chunk inside the tile
+        float* stg = stage_base + (g * 2 + (cc & 1)) * (STG_BYTES / 4);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + col0, r);
         tmem_ld_wait();
-        if (c == 1) {  // this warp has read all of its TMEM: hand the accumulator back to the MMA warp
+        if (c == NCHUNK - 1) {  // this warp has read all of its TMEM: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -346,15 +369,19 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 2D fp16 row-major [rows, cols] tensor, box = 64 columns x 128 rows, 128 B swizzle, zero fill out of bounds.
-int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols) {
+// Tile width used for an N-column GEMM (B operand = weights [N, K]): the widest of 256 / 192 / 128 that divides N.
+int gemm_tile_n(int N) { return N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128); }
+
+// 2D fp16 row-major [rows, cols] tensor, box = 64 columns x box_rows rows, 128 B swizzle, zero fill out of bounds.
+int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return DSS_ERR_CUDA;
   DSS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
   DSS_REQUIRE(cols % 8 == 0, "TMA operand row pitch must be a multiple of 16 bytes (cols=%d)", cols);
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  DSS_REQUIRE(box_rows > 0 && box_rows <= 256, "TMA box rows must be in [1, 256]");
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -366,13 +393,14 @@ int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols) {
   return DSS_OK;
 }
 
-template <int EPI>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& p,
-                     cudaStream_t st, int kclass, int batch = 1) {
+template <int EPI, int BN>
+static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& p,
+                        cudaStream_t st, int kclass, int batch) {
+  using Cfg = TileCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        GEMM_SMEM_BYTES));
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, BN);
@@ -381,9 +409,23 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int 
   if (sms <= 0) sms = 148;
   const int grid = total < sms ? total : sms;
   LaunchScope scope(st, kclass);
-  gemm_f16_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, tiles_m, tiles_n, total, p);
+  gemm_f16_tcgen05_kernel<EPI, BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, tiles_m, tiles_n,
+                                                                               total, p);
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
+}
+
+// bn = tile width the B tensor map was built for (its TMA box has bn rows)
+template <int EPI>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& p,
+                     cudaStream_t st, int kclass, int bn, int batch = 1) {
+  switch (bn) {
+    case 128: return launch_tc_bn<EPI, 128>(tmA, tmB, M, N, K, p, st, kclass, batch);
+    case 192: return launch_tc_bn<EPI, 192>(tmA, tmB, M, N, K, p, st, kclass, batch);
+    case 256: return launch_tc_bn<EPI, 256>(tmA, tmB, M, N, K, p, st, kclass, batch);
+  }
+  set_error("gemm: unsupported tile width %d", bn);
+  return DSS_ERR_BAD_ARG;
 }
 
 static int check_gemm_args(int M, int N, int K, int epi, const float* bias, const void* out, const float* aux,
@@ -400,17 +442,17 @@ static int check_gemm_args(int M, int N, int K, int epi, const float* bias, cons
 
 // Launch with pre-built tensor maps (used by the ViT forward, which caches them).
 int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* out, int M, int N, int K,
-                int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass) {
+                int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass, int bn) {
   int rc = check_gemm_args(M, N, K, epi, bias, out, aux, rin, rout);
   if (rc) return rc;
   EpiParams p{out, bias, aux, N, rin, rout, 0, nullptr, nullptr, 0.f, 0, 0};
   switch (epi) {
-    case DSS_EPI_BIAS_F16: return launch_tc<DSS_EPI_BIAS_F16>(tmA, tmB, M, N, K, p, st, kclass);
-    case DSS_EPI_BIAS_GELU_F16: return launch_tc<DSS_EPI_BIAS_GELU_F16>(tmA, tmB, M, N, K, p, st, kclass);
-    case DSS_EPI_BIAS_RESID_F32: return launch_tc<DSS_EPI_BIAS_RESID_F32>(tmA, tmB, M, N, K, p, st, kclass);
-    case DSS_EPI_BIAS_F32: return launch_tc<DSS_EPI_BIAS_F32>(tmA, tmB, M, N, K, p, st, kclass);
-    case DSS_EPI_PATCH_F32: return launch_tc<DSS_EPI_PATCH_F32>(tmA, tmB, M, N, K, p, st, kclass);
-    case DSS_EPI_DROPCLS_F32: return launch_tc<DSS_EPI_DROPCLS_F32>(tmA, tmB, M, N, K, p, st, kclass);
+    case DSS_EPI_BIAS_F16: return launch_tc<DSS_EPI_BIAS_F16>(tmA, tmB, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_BIAS_GELU_F16: return launch_tc<DSS_EPI_BIAS_GELU_F16>(tmA, tmB, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_BIAS_RESID_F32: return launch_tc<DSS_EPI_BIAS_RESID_F32>(tmA, tmB, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_BIAS_F32: return launch_tc<DSS_EPI_BIAS_F32>(tmA, tmB, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_PATCH_F32: return launch_tc<DSS_EPI_PATCH_F32>(tmA, tmB, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_DROPCLS_F32: return launch_tc<DSS_EPI_DROPCLS_F32>(tmA, tmB, M, N, K, p, st, kclass, bn);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return DSS_ERR_BAD_ARG;
@@ -423,7 +465,7 @@ int affinity_gemm_tc(const CUtensorMap& tmS, int images, int Nimg, int d, float*
                      cudaStream_t st) {
   EpiParams p{Wout, nullptr, nullptr, ldw, 0, 0, Nimg, img_max, counts, lambda, threshold, d / BK};
   DSS_REQUIRE(d % BK == 0, "affinity: feature dim must be a multiple of %d for the tensor-core path (got %d)", BK, d);
-  return launch_tc<EPI_AFFINITY_F32>(tmS, tmS, Nimg, ldw, 3 * d, p, st, KC_AFFINITY, images);
+  return launch_tc<EPI_AFFINITY_F32>(tmS, tmS, Nimg, ldw, 3 * d, p, st, KC_AFFINITY, 128, images);
 }
 
 template <int EPI>
@@ -447,10 +489,11 @@ extern "C" int dss_op_gemm_f16(const void* A, const void* Wt, const float* bias,
   if (rc) return rc;
   DSS_REQUIRE(A && Wt, "gemm: null operand");
   CUtensorMap tmA, tmB;
-  if ((rc = make_tmap_f16(&tmA, A, M, K))) return rc;
-  if ((rc = make_tmap_f16(&tmB, Wt, N, K))) return rc;
+  const int bn = gemm_tile_n(N);
+  if ((rc = make_tmap_f16(&tmA, A, M, K, BM))) return rc;
+  if ((rc = make_tmap_f16(&tmB, Wt, N, K, bn))) return rc;
   return gemm_f16_tc(tmA, tmB, bias, out, M, N, K, epilogue, aux, rin, rout, static_cast<cudaStream_t>(stream),
-                     KC_GEMM_OTHER);
+                     KC_GEMM_OTHER, bn);
 }
 
 extern "C" int dss_op_gemm_f16_simt(const void* A, const void* Wt, const float* bias, void* out, int M, int N, int K,

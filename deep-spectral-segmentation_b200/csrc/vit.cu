@@ -18,9 +18,10 @@
 
 namespace dss {
 
-int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols);
+int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
+int gemm_tile_n(int N);
 int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* out, int M, int N, int K,
-                int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass);
+                int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass, int bn);
 int launch_im2col(const uint8_t* img, void* patches, int B, int H, int W, int P, cudaStream_t st);
 int launch_cls_row(float* x, const float* cls, const float* pos, int B, int T, int d, cudaStream_t st);
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int M, int d, float eps, cudaStream_t st);
@@ -177,15 +178,15 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
 
   CUtensorMap tm_patches, tm_xn, tm_attn, tm_hid;
   const int Kp = 3 * P * P;
-  if ((rc = make_tmap_f16(&tm_patches, w.patches, B * Np, Kp))) return rc;
-  if ((rc = make_tmap_f16(&tm_xn, w.xn, M, d))) return rc;
-  if ((rc = make_tmap_f16(&tm_attn, w.attn, M, d))) return rc;
-  if ((rc = make_tmap_f16(&tm_hid, w.hid, M, c.mlp_ratio * d))) return rc;
+  if ((rc = make_tmap_f16(&tm_patches, w.patches, B * Np, Kp, 128))) return rc;
+  if ((rc = make_tmap_f16(&tm_xn, w.xn, M, d, 128))) return rc;
+  if ((rc = make_tmap_f16(&tm_attn, w.attn, M, d, 128))) return rc;
+  if ((rc = make_tmap_f16(&tm_hid, w.hid, M, c.mlp_ratio * d, 128))) return rc;
 
   // tokens: x[b, 1+n, :] = patch_embed + pos ; x[b, 0, :] = cls + pos[0]
   if ((rc = launch_im2col(img, w.patches, B, H, W, P, st))) return rc;
   if ((rc = gemm_f16_tc(tm_patches, h->tm_patch, h->patch_b, w.x, B * Np, d, Kp, DSS_EPI_PATCH_F32, pos, Np, T, st,
-                        KC_GEMM_PATCH)))
+                        KC_GEMM_PATCH, gemm_tile_n(d))))
     return rc;
   if ((rc = launch_cls_row(w.x, h->cls, pos, B, T, d, st))) return rc;
 
@@ -193,18 +194,18 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
     const BlockW& bw = h->blocks[l];
     if ((rc = launch_layernorm(w.x, bw.ln1_w, bw.ln1_b, w.xn, M, d, c.ln_eps, st))) return rc;
     if ((rc = gemm_f16_tc(tm_xn, bw.tm_qkv, bw.qkv_b, w.qkv, M, 3 * d, d, DSS_EPI_BIAS_F16, nullptr, 0, 0, st,
-                          KC_GEMM_QKV)))
+                          KC_GEMM_QKV, gemm_tile_n(3 * d))))
       return rc;
     if ((rc = launch_attention_tc(w.qkv, w.attn, B, T, c.heads, st))) return rc;
     if ((rc = gemm_f16_tc(tm_attn, bw.tm_proj, bw.proj_b, w.x, M, d, d, DSS_EPI_BIAS_RESID_F32, nullptr, 0, 0, st,
-                          KC_GEMM_PROJ)))
+                          KC_GEMM_PROJ, gemm_tile_n(d))))
       return rc;
     if ((rc = launch_layernorm(w.x, bw.ln2_w, bw.ln2_b, w.xn, M, d, c.ln_eps, st))) return rc;
     if ((rc = gemm_f16_tc(tm_xn, bw.tm_fc1, bw.fc1_b, w.hid, M, c.mlp_ratio * d, d, DSS_EPI_BIAS_GELU_F16, nullptr, 0,
-                          0, st, KC_GEMM_FC1)))
+                          0, st, KC_GEMM_FC1, gemm_tile_n(c.mlp_ratio * d))))
       return rc;
     if ((rc = gemm_f16_tc(tm_hid, bw.tm_fc2, bw.fc2_b, w.x, M, d, c.mlp_ratio * d, DSS_EPI_BIAS_RESID_F32, nullptr, 0,
-                          0, st, KC_GEMM_FC2)))
+                          0, st, KC_GEMM_FC2, gemm_tile_n(d))))
       return rc;
   }
   if (k_proj) {
@@ -212,7 +213,7 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
     if ((rc = launch_layernorm(w.x, bw.ln1_w, bw.ln1_b, w.xn, M, d, c.ln_eps, st))) return rc;
     // K third of the qkv projection (weight rows [d, 2d)), CLS rows dropped: out[b, n, :] == qkv[b, 1+n, d:2d]
     if ((rc = gemm_f16_tc(tm_xn, bw.tm_k, bw.qkv_b + d, out, M, d, d, DSS_EPI_DROPCLS_F32, nullptr, T, Np, st,
-                          KC_GEMM_KPROJ)))
+                          KC_GEMM_KPROJ, gemm_tile_n(d))))
       return rc;
   } else {
     DSS_CHECK_CUDA(cudaMemcpyAsync(out, w.x, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -290,7 +291,7 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
   h->patch_w = reinterpret_cast<__half*>(base + o_patch_w);
   h->patch_b = reinterpret_cast<float*>(base + o_patch_b);
   h->cls = reinterpret_cast<float*>(base + o_cls);
-  if ((rc = make_tmap_f16(&h->tm_patch, h->patch_w, (int)d, (int)Kp))) return rc;
+  if ((rc = make_tmap_f16(&h->tm_patch, h->patch_w, (int)d, (int)Kp, gemm_tile_n((int)d)))) return rc;
   h->blocks.resize(c.depth);
   for (int l = 0; l < c.depth; ++l) {
     const dss_vit_block_weights& s = w->blocks[l];
@@ -315,11 +316,11 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
     b.ln2_w = reinterpret_cast<float*>(base + bo[l].ln2_w); b.ln2_b = reinterpret_cast<float*>(base + bo[l].ln2_b);
     b.qkv_b = reinterpret_cast<float*>(base + bo[l].qkv_b); b.proj_b = reinterpret_cast<float*>(base + bo[l].proj_b);
     b.fc1_b = reinterpret_cast<float*>(base + bo[l].fc1_b); b.fc2_b = reinterpret_cast<float*>(base + bo[l].fc2_b);
-    if ((rc = make_tmap_f16(&b.tm_qkv, b.qkv_w, (int)(3 * d), (int)d))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_k, b.qkv_w + d * d, (int)d, (int)d))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_proj, b.proj_w, (int)d, (int)d))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_fc1, b.fc1_w, (int)hid, (int)d))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_fc2, b.fc2_w, (int)d, (int)hid))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_qkv, b.qkv_w, (int)(3 * d), (int)d, gemm_tile_n((int)(3 * d))))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_k, b.qkv_w + d * d, (int)d, (int)d, gemm_tile_n((int)d)))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_proj, b.proj_w, (int)d, (int)d, gemm_tile_n((int)d)))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_fc1, b.fc1_w, (int)hid, (int)d, gemm_tile_n((int)hid)))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_fc2, b.fc2_w, (int)d, (int)hid, gemm_tile_n((int)d)))) return rc;
   }
   // host copy of the positional grid for interpolation; drop stale interpolations
   const size_t npos = ((size_t)c.grid0 * c.grid0 + 1) * d;

@@ -94,36 +94,59 @@ def _load_image_lr(images_root: str, image_id: str, W_lr: int, H_lr: int) -> np.
 
 
 def _check_supported(which_matrix, which_color_matrix, image_color_lambda):
-    if which_matrix not in ("laplacian", "matting_laplacian"):
-        if which_matrix == "affinity_torch":
-            raise RuntimeError("which_matrix='affinity_torch' calls torch.eig, which PyTorch removed (dead in the reference)")
-        raise NotImplementedError(f"which_matrix={which_matrix!r}: only 'laplacian' / 'matting_laplacian' are built")
-    if image_color_lambda > 0 and which_color_matrix != "knn":
+    if which_matrix == "affinity_torch":
+        raise RuntimeError("which_matrix='affinity_torch' calls torch.eig, which PyTorch removed (dead in the reference)")
+    if which_matrix not in ("laplacian", "matting_laplacian", "affinity", "affinity_svd"):
+        raise ValueError(f"unknown which_matrix={which_matrix!r}")
+    if which_matrix in ("laplacian", "matting_laplacian") and image_color_lambda > 0 and which_color_matrix != "knn":
+        # 'rw' needs pymatting's _rw_laplacian, a third-party routine that is neither installed nor restatable offline
         raise NotImplementedError(f"which_color_matrix={which_color_matrix!r}: only 'knn' is built")
 
 
 def _eigs_for_group(data_dicts: List[dict], K: int, images_root, which_features, normalize, lapnorm, threshold_at_zero,
-                    image_downsample_factor, image_color_lambda, dev) -> Tuple[torch.Tensor, torch.Tensor]:
+                    image_downsample_factor, image_color_lambda, dev, which_matrix="laplacian"
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
     """One GPU batch: feature dicts whose patch grids have the same size -> (eigenvalues [B,K], eigenvectors [B,K,N]) CPU."""
     feats = torch.stack([d[which_features].squeeze() for d in data_dicts]).to(torch.float32)
-    rgb_lr, lr_size = None, None
-    sizes = utils.get_image_sizes(data_dicts[0])
-    P, H_patch, W_patch, H_pad, W_pad = sizes[4:]
-    factor = P if image_downsample_factor is None else image_downsample_factor
-    H_lr, W_lr = H_pad // factor, W_pad // factor
-    if (H_patch, W_patch) != (H_lr, W_lr):
-        raise NotImplementedError("image_downsample_factor != patch_size (feature up-sampling) is not built yet")
-    if image_color_lambda > 0:
-        lr = [_load_image_lr(images_root, d["file"][:-4], W_lr, H_lr) for d in data_dicts]
-        rgb_lr = torch.from_numpy(np.stack(lr).reshape(len(lr), H_lr * W_lr, 3).astype(np.float32)).to(dev)
-        lr_size = (H_lr, W_lr)
-    evals, evecs, info, _ = spectral.laplacian_eigs(feats.pin_memory().to(dev, non_blocking=True), K, normalize,
-                                                    threshold_at_zero, lapnorm, rgb_lr, lr_size, image_color_lambda)
+    feats = feats.pin_memory().to(dev, non_blocking=True)
+    if which_matrix in ("affinity", "affinity_svd"):
+        evals, evecs, info = spectral.affinity_eigs(feats, K, which_matrix, normalize, threshold_at_zero)
+    else:
+        rgb_lr, lr_size = None, None
+        sizes = utils.get_image_sizes(data_dicts[0])
+        P, H_patch, W_patch, H_pad, W_pad = sizes[4:]
+        factor = P if image_downsample_factor is None else image_downsample_factor
+        H_lr, W_lr = H_pad // factor, W_pad // factor
+        if (H_patch, W_patch) != (H_lr, W_lr):
+            # extract.py:148,179-188: normalise first, then bilinear up-sampling (no re-normalisation afterwards)
+            if normalize:
+                feats = spectral.normalize_rows(feats)
+                normalize = False
+            feats = spectral.upsample_bilinear(feats, H_patch, W_patch, H_lr, W_lr)
+        if image_color_lambda > 0:
+            lr = [_load_image_lr(images_root, d["file"][:-4], W_lr, H_lr) for d in data_dicts]
+            rgb_lr = torch.from_numpy(np.stack(lr).reshape(len(lr), H_lr * W_lr, 3).astype(np.float32)).to(dev)
+            lr_size = (H_lr, W_lr)
+        evals, evecs, info, _ = spectral.laplacian_eigs(feats, K, normalize, threshold_at_zero, lapnorm, rgb_lr,
+                                                        lr_size, image_color_lambda)
     evals, evecs, info = evals.cpu(), evecs.cpu(), info.cpu()
     bad = (info[:, 1] == 0).nonzero().flatten().tolist()
     if bad:
         print(f"Warning: eigensolver did not reach its tolerance for {[data_dicts[i]['id'] for i in bad]}")
+    if which_matrix == "affinity" and bool((info[:, 2] != 0).any()):
+        print("Warning: a negative eigenvalue exceeds the K-th largest in magnitude; eigsh(which='LM') would pick it")
     return evals, evecs
+
+
+def _save_eigs(output_file, which_matrix, evals_k: torch.Tensor, evecs_k: torch.Tensor):
+    """extract.py:242-244. The 'affinity' branch of the reference keeps `eigenvalues` as the ascending numpy array
+    eigsh returned while the eigenvectors are flipped to descending order (extract.py:171-172); mirrored here."""
+    if which_matrix == "affinity":
+        eigenvalues = evals_k.flip(0).numpy().copy()
+    else:
+        eigenvalues = evals_k.clone()
+    Path(output_file).parent.mkdir(parents=True, exist_ok=True)
+    torch.save({"eigenvalues": eigenvalues, "eigenvectors": evecs_k.clone()}, str(output_file))
 
 
 def _extract_eig(inp: Tuple[int, str], K: int, images_root: str, output_dir: str, which_matrix: str = "laplacian",
@@ -140,9 +163,8 @@ def _extract_eig(inp: Tuple[int, str], K: int, images_root: str, output_dir: str
         return
     _check_supported(which_matrix, which_color_matrix, image_color_lambda)
     evals, evecs = _eigs_for_group([data_dict], K, images_root, which_features, normalize, lapnorm, threshold_at_zero,
-                                   image_downsample_factor, image_color_lambda, _device())
-    Path(output_file).parent.mkdir(parents=True, exist_ok=True)
-    torch.save({"eigenvalues": evals[0].clone(), "eigenvectors": evecs[0].clone()}, output_file)
+                                   image_downsample_factor, image_color_lambda, _device(), which_matrix)
+    _save_eigs(output_file, which_matrix, evals[0], evecs[0])
 
 
 def extract_eigs(images_root: str, features_dir: str, output_dir: str, which_matrix: str = "laplacian",
@@ -179,11 +201,9 @@ def extract_eigs(images_root: str, features_dir: str, output_dir: str, which_mat
         if not dds:
             return
         evals, evecs = _eigs_for_group(dds, K, images_root, which_features, normalize, lapnorm, threshold_at_zero,
-                                       image_downsample_factor, image_color_lambda, dev)
+                                       image_downsample_factor, image_color_lambda, dev, which_matrix)
         for j, d in enumerate(dds):
-            out = Path(output_dir) / f"{d['file'][:-4]}.pth"
-            out.parent.mkdir(parents=True, exist_ok=True)
-            torch.save({"eigenvalues": evals[j].clone(), "eigenvectors": evecs[j].clone()}, str(out))
+            _save_eigs(Path(output_dir) / f"{d['file'][:-4]}.pth", which_matrix, evals[j], evecs[j])
 
     for index, features_file in inputs:
         data_dict = torch.load(str(features_file), map_location="cpu")

@@ -48,7 +48,7 @@ def knn_color_counts(rgb_lr: torch.Tensor, Hl: int, Wl: int) -> torch.Tensor:
 
 @torch.no_grad()
 def affinity(feats: torch.Tensor, normalize=True, threshold_at_zero=True, color_counts: Optional[torch.Tensor] = None,
-             color_lambda: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+             color_lambda: float = 0.0, out: Optional[torch.Tensor] = None, scale_by_max: bool = True) -> torch.Tensor:
     """feats [B, N, d] fp32 CUDA -> W [B, N, pitch(N)] fp32 (columns >= N are zero)."""
     _lib.require_cuda(feats, "feats")
     lib = _lib.load()
@@ -61,7 +61,8 @@ def affinity(feats: torch.Tensor, normalize=True, threshold_at_zero=True, color_
             out = torch.empty(B, N, ldw, dtype=torch.float32, device=dev)
         need = int(lib.dss_affinity_workspace_bytes(B, N, d))
         ws = _scratch.get("aff", need, dev)
-        flags = (_lib.AFF_NORMALIZE if normalize else 0) | (_lib.AFF_THRESHOLD_AT_ZERO if threshold_at_zero else 0)
+        flags = ((_lib.AFF_NORMALIZE if normalize else 0) | (_lib.AFF_THRESHOLD_AT_ZERO if threshold_at_zero else 0)
+                 | (0 if scale_by_max else _lib.AFF_NO_MAX_SCALE))
         cc = None
         if color_counts is not None and color_lambda > 0:
             cc = color_counts.contiguous()
@@ -91,6 +92,72 @@ def eigsh_laplacian(W: torch.Tensor, N: int, K: int, lapnorm=True, tol: float = 
                                            evals.data_ptr(), evecs.data_ptr(), info.data_ptr(), resid.data_ptr(),
                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "dss_eigsh_laplacian")
     return evals, evecs, info, resid
+
+
+@torch.no_grad()
+def eigsh_topk(A: torch.Tensor, N: int, K: int, tol: float = 0.0, max_steps: int = 0):
+    """A [B, N, lda] symmetric fp32 CUDA -> K algebraically largest pairs, descending:
+    (eigenvalues [B,K], eigenvectors [B,K,N] unit 2-norm with the sign rule, info [B,4], resid [B,K])."""
+    _lib.require_cuda(A, "A")
+    lib = _lib.load()
+    assert A.dtype == torch.float32 and A.is_contiguous() and A.dim() == 3 and A.shape[1] == N
+    B, _, lda = A.shape
+    dev = A.device
+    with torch.cuda.device(dev):
+        evals = torch.empty(B, K, dtype=torch.float32, device=dev)
+        evecs = torch.empty(B, K, N, dtype=torch.float32, device=dev)
+        info = torch.empty(B, 4, dtype=torch.int32, device=dev)
+        resid = torch.empty(B, K, dtype=torch.float32, device=dev)
+        need = int(lib.dss_eigsh_workspace_bytes(B, N, K, max_steps))
+        ws = _scratch.get("eig", need, dev)
+        _lib.check(lib.dss_eigsh_topk(A.data_ptr(), lda, B, N, K, float(tol), int(max_steps), evals.data_ptr(),
+                                      evecs.data_ptr(), info.data_ptr(), resid.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      _lib.stream_ptr(dev)), "dss_eigsh_topk")
+    return evals, evecs, info, resid
+
+
+@torch.no_grad()
+def normalize_rows(feats: torch.Tensor) -> torch.Tensor:
+    """F.normalize(p=2, dim=-1) of [..., d] fp32 CUDA features (extract.py:148)."""
+    _lib.require_cuda(feats, "feats")
+    f = feats.to(torch.float32).contiguous()
+    out = torch.empty_like(f)
+    with torch.cuda.device(f.device):
+        _lib.check(_lib.load().dss_normalize_rows(f.data_ptr(), f.numel() // f.shape[-1], f.shape[-1], out.data_ptr(),
+                                                  _lib.stream_ptr(f.device)), "dss_normalize_rows")
+    return out
+
+
+@torch.no_grad()
+def upsample_bilinear(feats: torch.Tensor, Hp: int, Wp: int, Hl: int, Wl: int) -> torch.Tensor:
+    """feats [B, Hp*Wp, d] -> [B, Hl*Wl, d]: F.interpolate(bilinear, align_corners=False) of extract.py:185-188."""
+    _lib.require_cuda(feats, "feats")
+    f = feats.to(torch.float32).contiguous()
+    B, N, d = f.shape
+    assert N == Hp * Wp
+    out = torch.empty(B, Hl * Wl, d, dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        _lib.check(_lib.load().dss_upsample_bilinear(f.data_ptr(), B, Hp, Wp, d, Hl, Wl, out.data_ptr(),
+                                                     _lib.stream_ptr(f.device)), "dss_upsample_bilinear")
+    return out
+
+
+@torch.no_grad()
+def affinity_eigs(feats: torch.Tensor, K: int, which_matrix: str = "affinity", normalize=True, threshold_at_zero=True,
+                  tol: float = 0.0, max_steps: int = 0):
+    """The reference's which_matrix='affinity' (eigsh(W, which='LM'), extract.py:166-172) and 'affinity_svd'
+    (torch.linalg.svd(feats), extract.py:160-163) branches for a batch. Returns descending (values, vectors, info);
+    for 'affinity_svd' the values are singular values sqrt(eig(F^ F^T))."""
+    if which_matrix == "affinity":
+        A = affinity(feats, normalize, threshold_at_zero, scale_by_max=False)
+    elif which_matrix == "affinity_svd":
+        A = affinity(feats, normalize, False, scale_by_max=False)
+    else:
+        raise ValueError(which_matrix)
+    evals, evecs, info, _ = eigsh_topk(A, feats.shape[1], K, tol, max_steps)
+    if which_matrix == "affinity_svd":
+        evals = evals.clamp_min(0).sqrt()
+    return evals, evecs, info
 
 
 @torch.no_grad()

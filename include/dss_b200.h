@@ -140,12 +140,13 @@ int dss_op_im2col_f16(const uint8_t* images_u8, void* patches, int B, int H, int
 /* ------------------------------------------------------------------------------------------------------------
  * Affinity + graph Laplacian eigensolver (replaces extract/extract.py:148,191-195,207-235,237-240)
  * ------------------------------------------------------------------------------------------------------------ */
-enum { DSS_AFF_NORMALIZE = 1, DSS_AFF_THRESHOLD_AT_ZERO = 2 };
+enum { DSS_AFF_NORMALIZE = 1, DSS_AFF_THRESHOLD_AT_ZERO = 2, DSS_AFF_NO_MAX_SCALE = 4 };
 
 size_t dss_affinity_workspace_bytes(int B, int N, int d);
 /* feats [B, N, d] fp32 -> Wmat [B, N, ldw] fp32 (row pitch ldw >= N, ldw % 4 == 0, pad columns written as 0):
  *   F^ = F / max(||F||, 1e-12) rowwise (if NORMALIZE)                      extract.py:148
  *   W  = F^ F^T ; W *= (W > 0) (if THRESHOLD) ; W /= max(W)                extract.py:191-194
+ *        (NO_MAX_SCALE skips the division: the 'affinity' / 'affinity_svd' branches, extract.py:160-172)
  *   W += color_counts * color_lambda  (if color_counts != NULL)            extract.py:213,221
  * color_counts [B, N, N] uint8 is the dense KNN colour affinity of dss_knn_color_counts. */
 int dss_affinity(const float* feats, int B, int N, int d, int flags, const uint8_t* color_counts, float color_lambda,
@@ -171,6 +172,21 @@ size_t dss_eigsh_workspace_bytes(int B, int N, int K, int max_steps);
 int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int K, int lapnorm, float tol, int max_steps,
                         float* evals, float* evecs, int* info, float* resid, void* ws, size_t ws_bytes,
                         dss_stream_t stream);
+
+/* K algebraically largest eigenpairs of the symmetric matrices Amat [B, N, lda], descending, unit 2-norm vectors,
+ * reference sign rule applied. Serves which_matrix='affinity' (eigsh(W, which='LM', k=K), extract.py:166-172; for a
+ * non-negative affinity the largest-magnitude eigenvalues are the largest positive ones -- info[b,2] is set to 1 if a
+ * negative eigenvalue of larger magnitude exists) and 'affinity_svd' (left singular vectors of F^ = eigenvectors of
+ * F^ F^T, extract.py:160-163). Same workspace / info / resid conventions as dss_eigsh_laplacian. */
+int dss_eigsh_topk(const float* Amat, int lda, int B, int N, int K, float tol, int max_steps, float* evals,
+                   float* evecs, int* info, float* resid, void* ws, size_t ws_bytes, dss_stream_t stream);
+
+/* Bilinear up-sampling of patch features (align_corners=False, as F.interpolate at extract.py:185-188):
+ * feats [B, Hp*Wp, d] fp32 -> out [B, Hl*Wl, d] fp32. Used when image_downsample_factor != patch size. */
+int dss_upsample_bilinear(const float* feats, int B, int Hp, int Wp, int d, int Hl, int Wl, float* out,
+                          dss_stream_t stream);
+/* Row-wise L2 normalisation x / max(||x||, 1e-12) (F.normalize, extract.py:148): feats [rows, d] -> out [rows, d]. */
+int dss_normalize_rows(const float* feats, int rows, int d, float* out, dss_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -123,8 +123,16 @@ def affinity_matrices(feats: torch.Tensor, normalize=True, threshold_at_zero=Tru
     return W_comb, D_comb
 
 
+def upsample_features(feats: torch.Tensor, grid, lr_size) -> torch.Tensor:
+    """extract.py:184-188 restated: (N, d) features on a (H_patch, W_patch) grid -> (H_lr*W_lr, d), bilinear."""
+    (Hp, Wp), (Hl, Wl) = grid, lr_size
+    return F.interpolate(feats.T.reshape(1, -1, Hp, Wp), size=(Hl, Wl), mode="bilinear",
+                         align_corners=False).reshape(-1, Hl * Wl).T
+
+
 def extract_eig(feats: torch.Tensor, K: int, which_matrix="laplacian", normalize=True, lapnorm=True,
-                threshold_at_zero=True, image_lr=None, image_color_lambda=0.0, knn=knn_exact, rng_seed=None):
+                threshold_at_zero=True, image_lr=None, image_color_lambda=0.0, knn=knn_exact, rng_seed=None,
+                grid=None, lr_size=None):
     """The arithmetic of reference ``_extract_eig`` from a feature tensor to (eigenvalues, eigenvectors).
 
     ``feats`` is the (1, N, d) / (N, d) float32 ``data_dict['k']``; ``image_lr`` the (H_lr, W_lr, 3) float64 /255
@@ -148,6 +156,12 @@ def extract_eig(feats: torch.Tensor, K: int, which_matrix="laplacian", normalize
         eigenvalues, eigenvectors = eigsh(W, which="LM", k=K, **kw)
         eigenvectors = torch.flip(torch.from_numpy(eigenvectors), dims=(-1,)).T
     elif which_matrix in ("matting_laplacian", "laplacian"):
+        if grid is not None and lr_size is not None and tuple(grid) != tuple(lr_size):
+            # extract.py:148 normalises BEFORE the up-sampling at :184-188 and never re-normalises
+            if normalize:
+                feats = F.normalize(feats, p=2, dim=-1)
+                normalize = False
+            feats = upsample_features(feats, grid, lr_size)
         W_comb, D_comb = affinity_matrices(feats, normalize, threshold_at_zero, image_lr, image_color_lambda, knn)
         if lapnorm:
             try:
