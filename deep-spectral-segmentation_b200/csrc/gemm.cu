@@ -12,6 +12,7 @@
 // Both operands are K-major, which is the native layout of activations [rows, features] and of torch Linear
 // weights [out, in]; no transposes anywhere.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -19,19 +20,28 @@ namespace dss {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;            // 4 TMEM lane quarters x 4 column slices
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-constexpr int STG_LD = 36;               // staging chunk: 128 rows x 32 cols fp32, row pitch 36 (conflict-free)
+constexpr int MANUAL_EPI_WARPS = 8;      // the row-remapping / affinity epilogues use the first 8 epilogue warps
+constexpr int STG_LD = 36;               // manual path staging chunk: 128 rows x 32 cols fp32, row pitch 36
 constexpr int STG_BYTES = BM * STG_LD * 4;
-// Tile width BN in {128, 192, 256}: wider tiles re-read the A rows less often from L2 (the K = 384 GEMMs of
-// ViT-S are L2 -> SM bandwidth bound at 128 x 128: 192 KB of operands per 12.6 MFLOP tile).
-template <int BN> struct TileCfg {
+constexpr int BOX_BYTES = BM * 128;      // TMA-store path staging box: 128 rows x 128 bytes (swizzled)
+
+// epilogues whose output rows are the GEMM rows: written with TMA (the row-remapping ones keep the manual path)
+__host__ __device__ constexpr bool epi_uses_tma_store(int epi) {
+  return epi == DSS_EPI_BIAS_F16 || epi == DSS_EPI_BIAS_GELU_F16 || epi == DSS_EPI_BIAS_RESID_F32 || epi == DSS_EPI_BIAS_F32;
+}
+constexpr int default_stages(int bn, bool tma) { return tma ? (bn == 128 ? 5 : 4) : (bn == 128 ? 4 : 3); }
+// The kernel is L2 -> SM bandwidth bound (~9.6 TB/s measured): a 128 x BN tile needs (128 + BN) * 128 B of operands
+// per 64-deep K slab, so wide tiles and a deep ring (bytes in flight) are what matter.
+template <int BN, bool TMA_OUT, int ST = default_stages(BN, TMA_OUT)> struct TileCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = BN == 128 ? 4 : 3;
+  static constexpr int STAGES = ST;
   static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;   // two fp32 accumulators, power-of-two allocation
-  // ring | 2 groups x 2 staging buffers | barriers | alignment slack
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + 256 + 1024;
+  static constexpr int STAGING_BYTES = TMA_OUT ? 2 * BOX_BYTES : 4 * STG_BYTES;
+  // ring | staging | barriers | alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
 };
 
 // Internal epilogue id (not part of the public enum): batched patch-affinity tile, see affinity.cu
@@ -59,7 +69,8 @@ struct EpiParams {
 // and Phi(x) = 1 - q for x >= 0, q for x < 0 (no cancellation on the negative side).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;  // MUFU.RCP (1 ulp); __frcp_rn would add a refinement step and a divergent special-case call per element
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);
   poly = fmaf(t, poly, -0.284496736f);
@@ -145,11 +156,12 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int tiles_m, int tiles_n
   return TileCoord{(rem / tiles_n) * BM, (rem % tiles_n) * BN, z};
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, int ST = default_stages(BN, epi_uses_tma_store(EPI))>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
-                        int N, int K, int tiles_m, int tiles_n, int total_tiles, EpiParams p) {
-  using Cfg = TileCfg<BN>;
+gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int tiles_m, int tiles_n,
+                        int total_tiles, EpiParams p) {
+  using Cfg = TileCfg<BN, epi_uses_tma_store(EPI), ST>;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, TMEM_COLS = Cfg::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment (the swizzle pattern is a function of address bits [7,10))
@@ -157,7 +169,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   float* stage_base = reinterpret_cast<float*>(gbase + STAGES * STAGE_BYTES);
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES + 4 * STG_BYTES;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES + Cfg::STAGING_BYTES;
   // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr(u32)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -165,7 +177,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * STAGES + 2 + i); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(gbase + STAGES * STAGE_BYTES + 4 * STG_BYTES + 8 * (2 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(gbase + STAGES * STAGE_BYTES + Cfg::STAGING_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -174,13 +186,14 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (epi_uses_tma_store(EPI)) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), EPI_WARPS);
+      mbar_init(tempty_bar(i), epi_uses_tma_store(EPI) ? EPI_WARPS : MANUAL_EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -246,11 +259,91 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
   } else {
     // epilogue: group g owns columns [g*BN/2, (g+1)*BN/2) of the tile; a warp may only touch TMEM lanes [32*(warp%4), +32)
-    constexpr int NCHUNK = BN / 64;            // 32-column chunks per group
     const int ew = warp - 2;
     const int g = ew >> 2, wq = ew & 3;
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    if constexpr (epi_uses_tma_store(EPI)) {
+      // ---- All 16 epilogue warps cooperate on one 128-byte-wide output box at a time (32 fp32 or 64 fp16 columns):
+      // warp (quarter q, slice sl) moves TMEM lanes [32q, 32q+32) x columns [sl*W, sl*W+W) -> registers -> +bias
+      // (-> GELU) -> two 16-byte chunks of the 128 B-swizzled staging box; one thread then issues the TMA store.
+      // The residual epilogue uses the TMA *reduce-add* (performed at the L2): x += acc + bias never reads x.
+      constexpr bool OUT16 = (EPI == DSS_EPI_BIAS_F16 || EPI == DSS_EPI_BIAS_GELU_F16);
+      constexpr int BOXC = OUT16 ? 64 : 32;          // columns per 128-byte-wide store box
+      constexpr int W = BOXC / 4;                    // columns per warp slice (16 fp16 / 8 fp32 = 32 bytes)
+      constexpr int NBOX = BN / BOXC;
+      const int sl = ew >> 2;
+      const bool issuer = (ew == 0) && (lane == 0);
+      const uint32_t stage_u32 = base + STAGES * STAGE_BYTES;
+      int lt = 0, cc = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const TileCoord tc = decode_tile<BN>(t, tiles_m, tiles_n);
+        const int buf = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(tfull_bar(buf), aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int b = 0; b < NBOX; ++b, ++cc) {
+          const int nc = tc.n0 + b * BOXC;           // first global column of the box
+          const bool live = nc < N;
+          float bias_r[W];                            // independent of the accumulator: issued before the TMEM wait
+#pragma unroll
+          for (int j = 0; j < W; j += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && live) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + sl * W + j));
+            bias_r[j] = bv.x; bias_r[j + 1] = bv.y; bias_r[j + 2] = bv.z; bias_r[j + 3] = bv.w;
+          }
+          uint32_t r[W];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + b * BOXC + sl * W;
+          if constexpr (OUT16) tmem_ld_32x16(taddr, r); else tmem_ld_32x8(taddr, r);
+          tmem_ld_wait();
+          if (b == NBOX - 1) {  // this warp has read all of its TMEM: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+          }
+          float x[W];
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            x[e] = __uint_as_float(r[e]) + bias_r[e];
+            if constexpr (EPI == DSS_EPI_BIAS_GELU_F16) x[e] = gelu_erf(x[e]);
+          }
+          // the staging box is free once the store issued two boxes ago has finished READING it
+          if (issuer) tma_store_wait_read<1>();
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+          const uint32_t sbuf = stage_u32 + (cc & 1) * BOX_BYTES;
+          const uint32_t srow = sbuf + row * 128;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {   // two 16-byte chunks per thread
+            const int j = sl * 2 + h;
+            const uint32_t addr = srow + ((j ^ (row & 7)) << 4);
+            if constexpr (OUT16) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_half2(x[h * 8 + 0], x[h * 8 + 1])),
+                           "r"(pack_half2(x[h * 8 + 2], x[h * 8 + 3])), "r"(pack_half2(x[h * 8 + 4], x[h * 8 + 5])),
+                           "r"(pack_half2(x[h * 8 + 6], x[h * 8 + 7]))
+                           : "memory");
+            } else {
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x[h * 4 + 0]), "f"(x[h * 4 + 1]),
+                           "f"(x[h * 4 + 2]), "f"(x[h * 4 + 3])
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+          if (issuer) {
+            if (live) {
+              if constexpr (EPI == DSS_EPI_BIAS_RESID_F32)
+                tma_reduce_add_2d(&tmC, sbuf, nc, tc.m0);
+              else
+                tma_store_2d(&tmC, sbuf, nc, tc.m0);
+            }
+            tma_store_commit();
+          }
+        }
+      }
+      if (issuer) tma_store_wait_all<0>();
+    } else if (ew < MANUAL_EPI_WARPS) {
+    constexpr int NCHUNK = BN / 64;            // 32-column chunks per group
     int lt = 0, cc = 0;  // cc: running chunk counter -> consecutive chunks always use alternate staging buffers
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const TileCoord tc = decode_tile<BN>(t, tiles_m, tiles_n);
@@ -288,7 +381,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
         // group-local barrier (ids 1, 2). Double-buffered staging: one barrier per chunk is enough, because a
         // thread reaches the barrier of chunk c only after finishing phase 2 of the previous user of buffer c^1.
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
         // Phase 2: 8 lanes x 16 B cover the 128 B of one row of the chunk, 4 rows per warp instruction
         if (nc < N) {
           const int cl = (lane & 7) * 4;
@@ -320,6 +413,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -369,8 +463,12 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// Tile width used for an N-column GEMM (B operand = weights [N, K]): the widest of 256 / 192 / 128 that divides N.
-int gemm_tile_n(int N) { return N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128); }
+// Tile width used for an N-column GEMM (B operand = weights [N, K]): 256 if it divides N, else 128.
+int gemm_tile_n(int N) {
+  static const char* force = getenv("DSS_GEMM_BN");  // tuning override (experiments only)
+  if (force) return atoi(force);
+  return N % 256 == 0 ? 256 : 128;
+}
 
 // 2D fp16 row-major [rows, cols] tensor, box = 64 columns x box_rows rows, 128 B swizzle, zero fill out of bounds.
 int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows) {
@@ -393,13 +491,35 @@ int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_
   return DSS_OK;
 }
 
-template <int EPI, int BN>
-static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& p,
-                        cudaStream_t st, int kclass, int batch) {
-  using Cfg = TileCfg<BN>;
+// Output tensor map for the TMA-store epilogues: row-major [rows, cols] of fp16 (box 64 x 128) or fp32 (box 32 x 128),
+// i.e. 128-byte-wide boxes with the 128 B swizzle.
+int make_tmap_out(CUtensorMap* tm, const void* ptr, int rows, int cols, int is_f32) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return DSS_ERR_CUDA;
+  DSS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA output must be 16-byte aligned");
+  const int esz = is_f32 ? 4 : 2;
+  DSS_REQUIRE((cols * esz) % 16 == 0, "TMA output row pitch must be a multiple of 16 bytes (cols=%d)", cols);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(is_f32 ? 32 : 64), (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed with CUresult %d (rows=%d cols=%d)", (int)r, rows, cols);
+    return DSS_ERR_CUDA;
+  }
+  return DSS_OK;
+}
+
+template <int EPI, int BN, int ST = default_stages(BN, epi_uses_tma_store(EPI))>
+static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, int M, int N, int K,
+                        const EpiParams& p, cudaStream_t st, int kclass, int batch) {
+  using Cfg = TileCfg<BN, epi_uses_tma_store(EPI), ST>;
   static bool attr_set = false;
   if (!attr_set) {
-    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<EPI, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -409,20 +529,23 @@ static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
   if (sms <= 0) sms = 148;
   const int grid = total < sms ? total : sms;
   LaunchScope scope(st, kclass);
-  gemm_f16_tcgen05_kernel<EPI, BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, tiles_m, tiles_n,
-                                                                               total, p);
+  if (epi_uses_tma_store(EPI) && tmC == nullptr) {
+    set_error("gemm: this epilogue needs an output tensor map");
+    return DSS_ERR_BAD_ARG;
+  }
+  gemm_f16_tcgen05_kernel<EPI, BN, ST><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmC ? *tmC : tmA, M, N, K,
+                                                                               tiles_m, tiles_n, total, p);
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
 }
 
 // bn = tile width the B tensor map was built for (its TMA box has bn rows)
 template <int EPI>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const EpiParams& p,
-                     cudaStream_t st, int kclass, int bn, int batch = 1) {
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, int M, int N, int K,
+                     const EpiParams& p, cudaStream_t st, int kclass, int bn, int batch = 1) {
   switch (bn) {
-    case 128: return launch_tc_bn<EPI, 128>(tmA, tmB, M, N, K, p, st, kclass, batch);
-    case 192: return launch_tc_bn<EPI, 192>(tmA, tmB, M, N, K, p, st, kclass, batch);
-    case 256: return launch_tc_bn<EPI, 256>(tmA, tmB, M, N, K, p, st, kclass, batch);
+    case 128: return launch_tc_bn<EPI, 128>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
+    case 256: return launch_tc_bn<EPI, 256>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
   }
   set_error("gemm: unsupported tile width %d", bn);
   return DSS_ERR_BAD_ARG;
@@ -441,18 +564,18 @@ static int check_gemm_args(int M, int N, int K, int epi, const float* bias, cons
 }
 
 // Launch with pre-built tensor maps (used by the ViT forward, which caches them).
-int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* out, int M, int N, int K,
-                int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass, int bn) {
+int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const float* bias, void* out,
+                int M, int N, int K, int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass, int bn) {
   int rc = check_gemm_args(M, N, K, epi, bias, out, aux, rin, rout);
   if (rc) return rc;
   EpiParams p{out, bias, aux, N, rin, rout, 0, nullptr, nullptr, 0.f, 0, 0};
   switch (epi) {
-    case DSS_EPI_BIAS_F16: return launch_tc<DSS_EPI_BIAS_F16>(tmA, tmB, M, N, K, p, st, kclass, bn);
-    case DSS_EPI_BIAS_GELU_F16: return launch_tc<DSS_EPI_BIAS_GELU_F16>(tmA, tmB, M, N, K, p, st, kclass, bn);
-    case DSS_EPI_BIAS_RESID_F32: return launch_tc<DSS_EPI_BIAS_RESID_F32>(tmA, tmB, M, N, K, p, st, kclass, bn);
-    case DSS_EPI_BIAS_F32: return launch_tc<DSS_EPI_BIAS_F32>(tmA, tmB, M, N, K, p, st, kclass, bn);
-    case DSS_EPI_PATCH_F32: return launch_tc<DSS_EPI_PATCH_F32>(tmA, tmB, M, N, K, p, st, kclass, bn);
-    case DSS_EPI_DROPCLS_F32: return launch_tc<DSS_EPI_DROPCLS_F32>(tmA, tmB, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_BIAS_F16: return launch_tc<DSS_EPI_BIAS_F16>(tmA, tmB, tmC, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_BIAS_GELU_F16: return launch_tc<DSS_EPI_BIAS_GELU_F16>(tmA, tmB, tmC, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_BIAS_RESID_F32: return launch_tc<DSS_EPI_BIAS_RESID_F32>(tmA, tmB, tmC, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_BIAS_F32: return launch_tc<DSS_EPI_BIAS_F32>(tmA, tmB, tmC, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_PATCH_F32: return launch_tc<DSS_EPI_PATCH_F32>(tmA, tmB, tmC, M, N, K, p, st, kclass, bn);
+    case DSS_EPI_DROPCLS_F32: return launch_tc<DSS_EPI_DROPCLS_F32>(tmA, tmB, tmC, M, N, K, p, st, kclass, bn);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return DSS_ERR_BAD_ARG;
@@ -465,7 +588,7 @@ int affinity_gemm_tc(const CUtensorMap& tmS, int images, int Nimg, int d, float*
                      cudaStream_t st) {
   EpiParams p{Wout, nullptr, nullptr, ldw, 0, 0, Nimg, img_max, counts, lambda, threshold, d / BK};
   DSS_REQUIRE(d % BK == 0, "affinity: feature dim must be a multiple of %d for the tensor-core path (got %d)", BK, d);
-  return launch_tc<EPI_AFFINITY_F32>(tmS, tmS, Nimg, ldw, 3 * d, p, st, KC_AFFINITY, 128, images);
+  return launch_tc<EPI_AFFINITY_F32>(tmS, tmS, nullptr, Nimg, ldw, 3 * d, p, st, KC_AFFINITY, 128, images);
 }
 
 template <int EPI>
@@ -492,8 +615,14 @@ extern "C" int dss_op_gemm_f16(const void* A, const void* Wt, const float* bias,
   const int bn = gemm_tile_n(N);
   if ((rc = make_tmap_f16(&tmA, A, M, K, BM))) return rc;
   if ((rc = make_tmap_f16(&tmB, Wt, N, K, bn))) return rc;
-  return gemm_f16_tc(tmA, tmB, bias, out, M, N, K, epilogue, aux, rin, rout, static_cast<cudaStream_t>(stream),
-                     KC_GEMM_OTHER, bn);
+  CUtensorMap tmC;
+  const bool tma_out = epi_uses_tma_store(epilogue);
+  if (tma_out) {
+    const int f32 = (epilogue == DSS_EPI_BIAS_RESID_F32 || epilogue == DSS_EPI_BIAS_F32) ? 1 : 0;
+    if ((rc = make_tmap_out(&tmC, out, M, N, f32))) return rc;
+  }
+  return gemm_f16_tc(tmA, tmB, tma_out ? &tmC : nullptr, bias, out, M, N, K, epilogue, aux, rin, rout,
+                     static_cast<cudaStream_t>(stream), KC_GEMM_OTHER, bn);
 }
 
 extern "C" int dss_op_gemm_f16_simt(const void* A, const void* Wt, const float* bias, void* out, int M, int N, int K,
@@ -512,5 +641,28 @@ extern "C" int dss_op_gemm_f16_simt(const void* A, const void* Wt, const float* 
     case DSS_EPI_DROPCLS_F32: return launch_simt<DSS_EPI_DROPCLS_F32>(A, Wt, M, N, K, p, st);
   }
   set_error("gemm: unknown epilogue %d", epilogue);
+  return DSS_ERR_BAD_ARG;
+}
+
+// Tuning probe (not used by the product path): plain bias epilogue with an explicit tile width / ring depth.
+extern "C" int dss_debug_gemm_cfg(const void* A, const void* Wt, const float* bias, void* out, int M, int N, int K,
+                                  int bn, int stages, dss_stream_t stream) {
+  int rc = check_gemm_args(M, N, K, DSS_EPI_BIAS_F16, bias, out, nullptr, 0, 0);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB, tmC;
+  if ((rc = make_tmap_f16(&tmA, A, M, K, BM))) return rc;
+  if ((rc = make_tmap_f16(&tmB, Wt, N, K, bn))) return rc;
+  if ((rc = make_tmap_out(&tmC, out, M, N, 0))) return rc;
+  EpiParams p{out, bias, nullptr, N, 0, 0, 0, nullptr, nullptr, 0.f, 0, 0};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int key = bn * 10 + stages;
+  switch (key) {
+    case 1283: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 3>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
+    case 1284: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 4>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
+    case 1285: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 5>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
+    case 2563: return launch_tc_bn<DSS_EPI_BIAS_F16, 256, 3>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
+    case 2564: return launch_tc_bn<DSS_EPI_BIAS_F16, 256, 4>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
+  }
+  set_error("debug_gemm_cfg: unsupported (bn=%d, stages=%d)", bn, stages);
   return DSS_ERR_BAD_ARG;
 }

@@ -20,8 +20,9 @@ namespace dss {
 
 int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
 int gemm_tile_n(int N);
-int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, void* out, int M, int N, int K,
-                int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass, int bn);
+int make_tmap_out(CUtensorMap* tm, const void* ptr, int rows, int cols, int is_f32);
+int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const float* bias, void* out,
+                int M, int N, int K, int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass, int bn);
 int launch_im2col(const uint8_t* img, void* patches, int B, int H, int W, int P, cudaStream_t st);
 int launch_cls_row(float* x, const float* cls, const float* pos, int B, int T, int d, cudaStream_t st);
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int M, int d, float eps, cudaStream_t st);
@@ -182,10 +183,15 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
   if ((rc = make_tmap_f16(&tm_xn, w.xn, M, d, 128))) return rc;
   if ((rc = make_tmap_f16(&tm_attn, w.attn, M, d, 128))) return rc;
   if ((rc = make_tmap_f16(&tm_hid, w.hid, M, c.mlp_ratio * d, 128))) return rc;
+  // output maps of the TMA-store epilogues: residual stream (fp32, reduce-add), qkv and MLP hidden (fp16)
+  CUtensorMap tm_x_out, tm_qkv_out, tm_hid_out;
+  if ((rc = make_tmap_out(&tm_x_out, w.x, M, d, 1))) return rc;
+  if ((rc = make_tmap_out(&tm_qkv_out, w.qkv, M, 3 * d, 0))) return rc;
+  if ((rc = make_tmap_out(&tm_hid_out, w.hid, M, c.mlp_ratio * d, 0))) return rc;
 
   // tokens: x[b, 1+n, :] = patch_embed + pos ; x[b, 0, :] = cls + pos[0]
   if ((rc = launch_im2col(img, w.patches, B, H, W, P, st))) return rc;
-  if ((rc = gemm_f16_tc(tm_patches, h->tm_patch, h->patch_b, w.x, B * Np, d, Kp, DSS_EPI_PATCH_F32, pos, Np, T, st,
+  if ((rc = gemm_f16_tc(tm_patches, h->tm_patch, nullptr, h->patch_b, w.x, B * Np, d, Kp, DSS_EPI_PATCH_F32, pos, Np, T, st,
                         KC_GEMM_PATCH, gemm_tile_n(d))))
     return rc;
   if ((rc = launch_cls_row(w.x, h->cls, pos, B, T, d, st))) return rc;
@@ -193,18 +199,18 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
   for (int l = 0; l < n_full; ++l) {
     const BlockW& bw = h->blocks[l];
     if ((rc = launch_layernorm(w.x, bw.ln1_w, bw.ln1_b, w.xn, M, d, c.ln_eps, st))) return rc;
-    if ((rc = gemm_f16_tc(tm_xn, bw.tm_qkv, bw.qkv_b, w.qkv, M, 3 * d, d, DSS_EPI_BIAS_F16, nullptr, 0, 0, st,
+    if ((rc = gemm_f16_tc(tm_xn, bw.tm_qkv, &tm_qkv_out, bw.qkv_b, w.qkv, M, 3 * d, d, DSS_EPI_BIAS_F16, nullptr, 0, 0, st,
                           KC_GEMM_QKV, gemm_tile_n(3 * d))))
       return rc;
     if ((rc = launch_attention_tc(w.qkv, w.attn, B, T, c.heads, st))) return rc;
-    if ((rc = gemm_f16_tc(tm_attn, bw.tm_proj, bw.proj_b, w.x, M, d, d, DSS_EPI_BIAS_RESID_F32, nullptr, 0, 0, st,
+    if ((rc = gemm_f16_tc(tm_attn, bw.tm_proj, &tm_x_out, bw.proj_b, w.x, M, d, d, DSS_EPI_BIAS_RESID_F32, nullptr, 0, 0, st,
                           KC_GEMM_PROJ, gemm_tile_n(d))))
       return rc;
     if ((rc = launch_layernorm(w.x, bw.ln2_w, bw.ln2_b, w.xn, M, d, c.ln_eps, st))) return rc;
-    if ((rc = gemm_f16_tc(tm_xn, bw.tm_fc1, bw.fc1_b, w.hid, M, c.mlp_ratio * d, d, DSS_EPI_BIAS_GELU_F16, nullptr, 0,
+    if ((rc = gemm_f16_tc(tm_xn, bw.tm_fc1, &tm_hid_out, bw.fc1_b, w.hid, M, c.mlp_ratio * d, d, DSS_EPI_BIAS_GELU_F16, nullptr, 0,
                           0, st, KC_GEMM_FC1, gemm_tile_n(c.mlp_ratio * d))))
       return rc;
-    if ((rc = gemm_f16_tc(tm_hid, bw.tm_fc2, bw.fc2_b, w.x, M, d, c.mlp_ratio * d, DSS_EPI_BIAS_RESID_F32, nullptr, 0,
+    if ((rc = gemm_f16_tc(tm_hid, bw.tm_fc2, &tm_x_out, bw.fc2_b, w.x, M, d, c.mlp_ratio * d, DSS_EPI_BIAS_RESID_F32, nullptr, 0,
                           0, st, KC_GEMM_FC2, gemm_tile_n(d))))
       return rc;
   }
@@ -212,7 +218,7 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
     const BlockW& bw = h->blocks[n_full];
     if ((rc = launch_layernorm(w.x, bw.ln1_w, bw.ln1_b, w.xn, M, d, c.ln_eps, st))) return rc;
     // K third of the qkv projection (weight rows [d, 2d)), CLS rows dropped: out[b, n, :] == qkv[b, 1+n, d:2d]
-    if ((rc = gemm_f16_tc(tm_xn, bw.tm_k, bw.qkv_b + d, out, M, d, d, DSS_EPI_DROPCLS_F32, nullptr, T, Np, st,
+    if ((rc = gemm_f16_tc(tm_xn, bw.tm_k, nullptr, bw.qkv_b + d, out, M, d, d, DSS_EPI_DROPCLS_F32, nullptr, T, Np, st,
                           KC_GEMM_KPROJ, gemm_tile_n(d))))
       return rc;
   } else {
