@@ -1,16 +1,20 @@
 // Multi-head attention (head dim 64) on the 5th-generation tensor cores: O = softmax(Q K^T / 8) V.
 //
-// One CTA = one (image, head, 128-query tile). Flash-style loop over 128-key tiles:
+// One CTA = one (image, head, 128-query tile), one CTA per SM, software-pipelined flash-style loop over 128-key tiles:
 //   warp 0      TMA producer: Q once, then K_j / V_j tiles straight out of the packed qkv activations
-//               [B*T, 3d] (box 64 x 128, 128 B swizzle) through a 2-stage ring
+//               [B*T, 3d] (box 64 x 128, 128 B swizzle) through a 3-stage ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
-//                 S   = Q K_j^T   (UMMA 128x128x16 x4, both operands K-major)            -> TMEM cols [0,128)
-//                 O_j = P_j V_j   (UMMA 128x64x16  x8, A = P from smem, B = V MN-major)   -> TMEM cols [128,192)
-//   warps 2..5  softmax / accumulate: thread = query row (tcgen05.ld 32x32b), running max / sum in base 2,
-//               P_j written as fp16 into the K-major 128 B-swizzled smem tile the PV MMA reads, and the output
-//               accumulated in REGISTERS: O = O * 2^(m_old - m_new) + O_j, so TMEM is never rescaled in place.
-// Two CTAs are resident per SM (96 KB smem, 256 TMEM columns each): while one CTA's softmax warps are busy
-// (MUFU-bound: 128x128 exp2 per tile) the other CTA's MMAs run.
+//                 S_j = Q K_j^T   (UMMA 128x128x16 x4, both operands K-major)            -> TMEM S[j & 1]
+//                 O_j = P_j V_j   (UMMA 128x64x16  x8, A = P from smem, B = V MN-major)   -> TMEM O[j & 1]
+//               S_{j+1} is issued BEFORE waiting for P_j, so the tensor core computes the next score tile while the
+//               softmax warps work on the current one; S, O and P are all double buffered.
+//   warps 2..9  softmax / accumulate: TWO threads per query row (tcgen05.ld 32x32b): warps 2..5 own keys 0..63 and
+//               head dims 0..31, warps 6..9 keys 64..127 and head dims 32..63; the partial row maxima are exchanged
+//               through shared memory. Running max / sum in base 2, P_j written as fp16 into the K-major 128 B-
+//               swizzled smem tiles the PV MMA reads. The output is accumulated in REGISTERS one tile late
+//               (O = O * 2^(m_{j-2} - m_{j-1}) + O_{j-1} while tile j is in flight), so the softmax warps never
+//               wait for a tensor-core result that was issued in the same iteration.
+// The kernel is bound by the MUFU pipe (128 x 128 exp2 per tile at 16 per clock per SM), not by the tensor pipe.
 #include <math.h>
 
 #include "common.cuh"
@@ -19,27 +23,38 @@ namespace dss {
 
 int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
 
-constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64, FA_THREADS = 192;
-constexpr int FA_TILE = FA_BM * FA_D * 2;             // 16 KB: one [128 x 64] fp16 tile
-constexpr int FA_SMEM = FA_TILE * (1 + 2 + 2 + 1);  // Q | K0 K1 | V0 V1 | P(keys 64..127) = 96 KB; P(keys 0..63) reuses K_j
-constexpr int FA_TMEM_COLS = 256;
-constexpr int FA_S_COL = 0, FA_O_COL = 128;
+// one MUFU.EX2 (2 ulp), flushes denormal results to zero; exp2f would add range checks and fix-ups per element
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
+constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64, FA_THREADS = 320;   // TMA warp + MMA warp + 8 softmax warps
+constexpr int FA_TILE = FA_BM * FA_D * 2;             // 16 KB: one [128 x 64] fp16 tile
+constexpr int FA_KV_STAGES = 3;
+constexpr int FA_SMEM = FA_TILE * (1 + 2 * FA_KV_STAGES + 4);  // Q | K ring | V ring | P[2] (2 atoms each) = 176 KB
+constexpr int FA_TMEM_COLS = 512;
+constexpr int FA_S_COL = 0, FA_O_COL = 256;   // S[2] at columns 0 / 128, O[2] at columns 256 / 320
+
+__global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int heads) {
   extern __shared__ __align__(1024) uint8_t fa_smem[];
-  __shared__ __align__(8) uint64_t bars[9];  // q_full | kv_full[2] | kv_empty[2] | s_full | p_full | o_full | (pad)
+  __shared__ __align__(8) uint64_t bars[1 + 2 * FA_KV_STAGES + 6];  // q_full | kv_full[] | kv_empty[] | s_full[2] | p_full[2] | o_full[2]
   __shared__ uint32_t tmem_ptr_s;
+  __shared__ float xch[2][2][FA_BM];   // [tile parity][key half][row]: partial row maxima (and the final row sums)
 
   const uint32_t base = smem_u32(fa_smem);
   if ((base & 1023u) != 0) __trap();  // the 128 B swizzle pattern is a function of address bits [7,10)
-  // P_j (128 queries x 128 keys fp16 = two 64-key atoms): atom 0 overwrites K_j, which is dead once S_j = Q K_j^T has
-  // completed (s_full) and is not refilled before PV_j has completed (kv_empty); atom 1 has its own buffer.
-  const uint32_t sQ = base, sK = base + FA_TILE, sV = base + 3 * FA_TILE, sP1 = base + 5 * FA_TILE;
+  // P_j = 128 queries x 128 keys fp16 = two 64-key atoms of 16 KB; double buffered
+  const uint32_t sQ = base, sK = base + FA_TILE, sV = sK + FA_KV_STAGES * FA_TILE, sP = sV + FA_KV_STAGES * FA_TILE;
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t q_full = bar0, s_full = bar0 + 40, p_full = bar0 + 48, o_full = bar0 + 56;
+  const uint32_t q_full = bar0;
   auto kv_full = [&](int s) { return bar0 + 8u + 8u * s; };
-  auto kv_empty = [&](int s) { return bar0 + 24u + 8u * s; };
+  auto kv_empty = [&](int s) { return bar0 + 8u + 8u * (FA_KV_STAGES + s); };
+  auto s_full = [&](int i) { return bar0 + 8u + 8u * (2 * FA_KV_STAGES + i); };
+  auto p_full = [&](int i) { return bar0 + 8u + 8u * (2 * FA_KV_STAGES + 2 + i); };
+  auto o_full = [&](int i) { return bar0 + 8u + 8u * (2 * FA_KV_STAGES + 4 + i); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -51,13 +66,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < FA_KV_STAGES; ++s) {
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i), 256);
+      mbar_init(o_full(i), 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -74,8 +91,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
       mbar_arrive_expect_tx(q_full, FA_TILE);
       tma_load_2d(sQ, &tmQKV, q_full, h * FA_D, row0 + q0);
       for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int s = j % FA_KV_STAGES;
+        const uint32_t ph = (j / FA_KV_STAGES) & 1;
         mbar_wait(kv_empty(s), ph ^ 1u);
         mbar_arrive_expect_tx(kv_full(s), 2 * FA_TILE);
         tma_load_2d(sK + s * FA_TILE, &tmQKV, kv_full(s), d + h * FA_D, row0 + j * FA_BN);
@@ -87,143 +104,135 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
       constexpr uint32_t idesc_qk = umma_idesc_f16(FA_BM, FA_BN);                 // A, B K-major
       constexpr uint32_t idesc_pv = umma_idesc_f16(FA_BM, FA_D) | (1u << 16);     // B (= V) MN-major
       mbar_wait(q_full, 0);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(kv_full(s), ph);
+      auto issue_s = [&](int j) {   // S[j & 1] = Q K_j^T
+        const int s = j % FA_KV_STAGES;
+        mbar_wait(kv_full(s), (j / FA_KV_STAGES) & 1);
         tc_fence_after();
-        // S = Q K^T. The S columns are free: softmax of tile j-1 finished reading them before p_full(j-1).
 #pragma unroll
         for (int k = 0; k < FA_D / 16; ++k)
-          umma_f16_ss(tmem_base + FA_S_COL, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(sK + s * FA_TILE + k * 32),
-                      idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(s_full);
-        // O_j = P_j V_j once the softmax warps have published P_j (and consumed O_{j-1})
-        mbar_wait(p_full, j & 1);
+          umma_f16_ss(tmem_base + FA_S_COL + (j & 1) * FA_BN, umma_desc_sw128(sQ + k * 32),
+                      umma_desc_sw128(sK + s * FA_TILE + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(s_full(j & 1));
+      };
+      issue_s(0);
+      for (int j = 0; j < nt; ++j) {
+        // next score tile first: its S buffer was released by p_full(j-1), observed in the previous iteration
+        if (j + 1 < nt) issue_s(j + 1);
+        // O[j & 1] = P_j V_j once the softmax warps have published P_j (they consumed O_{j-2} before that)
+        mbar_wait(p_full(j & 1), (j >> 1) & 1);
         tc_fence_after();
+        const int s = j % FA_KV_STAGES;
+        const uint32_t pj = sP + (j & 1) * 2 * FA_TILE;
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k) {
-          const uint32_t patom = (k >> 2) ? sP1 : sK + s * FA_TILE;                        // 64-key atoms, K-major
-          const uint64_t adesc = umma_desc_sw128(patom + (k & 3) * 32);
+          const uint64_t adesc = umma_desc_sw128(pj + (k >> 2) * FA_TILE + (k & 3) * 32);   // 64-key atoms, K-major
           const uint64_t bdesc = umma_desc_sw128(sV + s * FA_TILE + k * 16 * 128);          // 16 key rows per step
-          umma_f16_ss(tmem_base + FA_O_COL, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + FA_O_COL + (j & 1) * FA_D, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
         }
-        umma_commit(o_full);
+        umma_commit(o_full(j & 1));
         umma_commit(kv_empty(s));
       }
     }
   } else {
     const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int hs = (warp - 2) >> 2;       // 0: keys 0..63 / head dims 0..31, 1: keys 64..127 / head dims 32..63
     const int r = q * 32 + lane;          // query row inside the tile
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float sc = 1.4426950408889634f * 0.125f;  // log2(e) / sqrt(64)
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[FA_D];
+    float m_run = -INFINITY, l_run = 0.f;  // l_run: this thread's half of the row sum
+    float corr_prev = 0.f;                 // rescale factor that goes with the not-yet-accumulated O_{j-1}
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
-    for (int j = 0; j < nt; ++j) {
-      mbar_wait(s_full, j & 1);
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    auto accumulate_o = [&](int jj, float corr) {   // o = o * corr + O_jj  (head dims [32 hs, 32 hs + 32))
+      mbar_wait(o_full(jj & 1), (jj >> 1) & 1);
       tc_fence_after();
-      const int nvalid = T - j * FA_BN;   // keys of this tile that exist (>= 128 except for the last tile)
-      const bool full_tile = nvalid >= FA_BN;
-      const uint32_t prow0 = sK + (j & 1) * FA_TILE + r * 128;   // this row inside P atom 0 (keys 0..63)
-      const uint32_t prow1 = sP1 + r * 128;                      // ... and atom 1 (keys 64..127)
-      // pass 1: row maximum (two 32-column TMEM loads in flight per wait)
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < 4; c += 2) {
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(lane_addr + FA_S_COL + c * 32, v0);
-        tmem_ld_32x32(lane_addr + FA_S_COL + c * 32 + 32, v1);
+      uint32_t v[32];
+      tmem_ld_32x32(lane_addr + FA_O_COL + (jj & 1) * FA_D + hs * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
+    };
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(s_full(j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      const int nvalid = T - j * FA_BN - hs * 64;   // keys of this thread's half tile that exist
+      const bool full_tile = nvalid >= 64;
+      // this row inside the P atom of this half (P[j & 1] was last read by PV_{j-2}: complete, see accumulate_o below)
+      const uint32_t prow = sP + ((j & 1) * 2 + hs) * FA_TILE + r * 128;
+      const uint32_t scol = lane_addr + FA_S_COL + (j & 1) * FA_BN + hs * 64;
+      // this thread's 64 scores are read from TMEM ONCE and stay in registers (TMEM -> RF bandwidth is the scarce
+      // resource of this kernel after the MUFU pipe)
+      uint32_t v[64];
+      {
+        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+        tmem_ld_32x32(scol, v0);
+        tmem_ld_32x32(scol + 32, v1);
         tmem_ld_wait();
-        if (full_tile) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v0[i]));
-            if (c * 32 + 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v1[i]));
-          }
-        }
       }
-      const float corr = exp2f((m_run - mx) * sc);   // first tile: exp2(-inf) = 0
+      // row maximum over this half, exchanged with the thread owning the other half
+      if (!full_tile) {   // keys beyond T (only in the last tile): score -inf -> probability exactly 0
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= nvalid) v[i] = 0xff800000u;
+      }
+      float mxp = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mxp = fmaxf(mxp, __uint_as_float(v[i]));
+      xch[j & 1][hs][r] = mxp;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float mx = fmaxf(m_run, fmaxf(mxp, xch[j & 1][hs ^ 1][r]));
+      const float corr = ex2_approx((m_run - mx) * sc);   // first tile: exp2(-inf) = 0
       const float msc = mx * sc;
       m_run = mx;
-      // pass 2: P = 2^(s*c - m*c), row sum, fp16 P into the swizzled K-major tiles
+      // P = 2^(s*c - m*c), partial row sum, fp16 P into the swizzled K-major tile of this half
       float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + FA_S_COL + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (full_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = exp2f(fmaf(__uint_as_float(v[i]), sc, -msc));
-            const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), sc, -msc));
-            rs += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
-          }
-        } else {
+      for (int g = 0; g < 8; ++g) {   // 8 chunks of 8 keys = 16 bytes each; chunk g of the row sits at slot g ^ (r % 8)
+        uint32_t pk[4];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c * 32 + i < nvalid) ? exp2f(fmaf(__uint_as_float(v[i]), sc, -msc)) : 0.f;
-            const float p1 = (c * 32 + i + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sc, -msc)) : 0.f;
-            rs += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
-          }
+        for (int e = 0; e < 8; e += 2) {
+          const int i = g * 8 + e;
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -msc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -msc));
+          rs += p0 + p1;
+          pk[e >> 1] = pack_half2(p0, p1);
         }
-        // keys [32c, 32c+32) = 4 chunks of 8 keys; chunk g of the row: atom g/8, slot (g%8) ^ (r%8)
-        const uint32_t prow = (c < 2) ? prow0 : prow1;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int g = (c & 1) * 4 + t;
-          const uint32_t addr = prow + (((g ^ (r & 7))) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[t * 4 + 0]), "r"(pk[t * 4 + 1]),
-                       "r"(pk[t * 4 + 2]), "r"(pk[t * 4 + 3])
-                       : "memory");
-        }
+        const uint32_t addr = prow + (((g ^ (r & 7))) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                     : "memory");
       }
       l_run = l_run * corr + rs;
       fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
-      tc_fence_before();          // order the TMEM reads of S before the next S MMA
-      mbar_arrive(p_full);
-      // O = O * corr + P_j V_j
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-      {
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(lane_addr + FA_O_COL, v0);
-        tmem_ld_32x32(lane_addr + FA_O_COL + 32, v1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          o[i] = fmaf(o[i], corr, __uint_as_float(v0[i]));
-          o[32 + i] = fmaf(o[32 + i], corr, __uint_as_float(v1[i]));
-        }
-      }
-      tc_fence_before();          // O_j consumed before PV_{j+1} may overwrite it (ordered via p_full(j+1))
+      tc_fence_before();          // order the TMEM reads of S_j (and of O_{j-2}) before the MMAs that overwrite them
+      mbar_arrive(p_full(j & 1));
+      // accumulate the PREVIOUS tile's P V product (issued one iteration ago, so normally already complete)
+      if (j > 0) accumulate_o(j - 1, corr_prev);
+      corr_prev = corr;
     }
-    // epilogue: normalise, stage the [128 x 64] fp16 tile in the (now idle) P buffer, store coalesced
-    const float inv = 1.0f / l_run;
-    uint8_t* stage = fa_smem + FA_TILE;       // K/V ring is idle now; rows of 128 B + 16 B pad -> conflict-free writes
+    accumulate_o(nt - 1, corr_prev);
+    // epilogue: total row sum = sum of the two halves; normalise, stage the [128 x 64] fp16 tile in the (now idle)
+    // K/V ring, store coalesced
+    xch[nt & 1][hs][r] = l_run;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const float inv = 1.0f / (l_run + xch[nt & 1][hs ^ 1][r]);
+    uint8_t* stage = fa_smem + FA_TILE;       // rows of 128 B + 16 B pad -> conflict-free row-per-thread writes
 #pragma unroll
-    for (int i = 0; i < FA_D; i += 8) {
+    for (int i = 0; i < 32; i += 8) {
       uint4 w;
       w.x = pack_half2(o[i + 0] * inv, o[i + 1] * inv);
       w.y = pack_half2(o[i + 2] * inv, o[i + 3] * inv);
       w.z = pack_half2(o[i + 4] * inv, o[i + 5] * inv);
       w.w = pack_half2(o[i + 6] * inv, o[i + 7] * inv);
-      *reinterpret_cast<uint4*>(stage + r * 144 + i * 2) = w;
+      *reinterpret_cast<uint4*>(stage + r * 144 + hs * 64 + i * 2) = w;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 2, 256;" ::: "memory");
     const int ew = warp - 2;
     __half* og = out + (long long)row0 * d + h * FA_D;
 #pragma unroll 4
-    for (int it = 0; it < 8; ++it) {
-      const int rr = ew * 32 + it * 4 + (lane >> 3);    // 4 rows per warp instruction, 8 lanes x 16 B per row
+    for (int it = 0; it < 4; ++it) {
+      const int rr = ew * 16 + it * 4 + (lane >> 3);    // 4 rows per warp instruction, 8 lanes x 16 B per row
       const int t = q0 + rr;
       if (t < T) {
         const uint4 w = *reinterpret_cast<const uint4*>(stage + rr * 144 + (lane & 7) * 16);
