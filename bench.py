@@ -61,7 +61,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -339,8 +339,13 @@ def run_ours(args, rank, local_rank, world):
     dom = next((k for k in kernels if "bound" in k), None)
     roofline = None
     if dom:
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed ncu capture
+            traffic = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text()).get(dom["kernel"])
+        except Exception:
+            pass
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
-                    "unit": dom["unit"], "frac": dom["frac"], "traffic": None, "share_of_step": dom["share"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "share_of_step": dom["share"],
                     "peak_source": peaks["source"] + (", sustained bf16 GEMM" if dom["bound"] == "tensor" else ""),
                     "timing": "CUDA events around every launch of the class in a separate instrumented pass of the same steps"}
 
