@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--size", type=int, default=480)
     ap.add_argument("--K", type=int, default=5)
     ap.add_argument("--model", default="dino_vits16")
-    ap.add_argument("--vit-batch", type=int, default=32)
+    ap.add_argument("--vit-batch", type=int, default=0, help="images per ViT launch sequence (0 = the whole step)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images of the CPU-baseline sample (0 = 2 x workers)")
     ap.add_argument("--parity-sample", type=int, default=4)
     ap.add_argument("--ref-images-per-step", type=int, default=0, help="0 = 2 x worker processes")
@@ -233,6 +233,8 @@ def run_ours(args, rank, local_rank, world):
     # the one collective of the path: DINO weights from rank 0
     sd0 = vit.random_state_dict(args.model, 0) if rank == 0 else None
     sd = pipeline.broadcast_weights(args.model, 0, device=dev, src=0, state_dict=sd0)
+    if args.vit_batch <= 0:
+        args.vit_batch = args.images_per_step
     pipe = pipeline.SpectralPipeline(args.model, K=args.K, device=dev, state_dict=sd, vit_batch=args.vit_batch)
     P, d, depth = pipe.model.patch_size, pipe.model.dim, pipe.model.depth
     B, S, K = args.images_per_step, args.size, args.K
@@ -276,14 +278,15 @@ def run_ours(args, rank, local_rank, world):
     conv = int(info[:, 1].sum().item())
     steps_mean = float(info[:, 0].float().mean().item())
 
-    # ---- end to end through the host-buffer call
-    for _ in range(2):
-        pipe.run_host(host_imgs)
+    # ---- end to end through the host-buffer call: every step copies its uint8 images from pinned host memory and
+    # brings the eigenvectors back; the streaming driver overlaps step i+1's H2D and step i-1's D2H with step i
+    for _ in pipe.run_host_pipelined([host_imgs] * 2):
+        pass
     barrier()
     e0.record()
     out = None
-    for _ in range(args.steps):
-        out = pipe.run_host(host_imgs)
+    for out in pipe.run_host_pipelined([host_imgs] * args.steps):
+        pass
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))

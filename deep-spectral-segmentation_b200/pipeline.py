@@ -118,6 +118,50 @@ class SpectralPipeline:
         cur.synchronize()
         return h_evals, h_evecs, h_info
 
+    @torch.no_grad()
+    def run_host_pipelined(self, batches, copy_chunk: int = 32):
+        """Streaming form of run_host for a sequence of equally shaped HOST batches: the H2D copy of batch i+1 runs
+        on the copy stream while batch i is being computed, and the D2H of batch i completes while batch i+1 runs.
+        Yields (eigenvalues, eigenvectors, info) per batch, in order; the yielded tensors are pinned buffers that stay
+        valid until two further batches have been submitted."""
+        cur = torch.cuda.current_stream(self.device)
+        done = [None, None]      # per slot: event recorded after the D2H of the batch that used the slot
+        pending = None           # (slot, outputs) of the previous batch
+        for i, hb in enumerate(batches):
+            assert not hb.is_cuda and hb.dtype == torch.uint8
+            slot = i & 1
+            B = hb.shape[0]
+            dev_imgs = self._buf(("imgs", slot), tuple(hb.shape), torch.uint8)
+            if done[slot] is not None:
+                self._copy_stream.wait_event(done[slot])   # the batch that used this slot two steps ago is finished
+            vb = self.vit_batch
+            events = []
+            with torch.cuda.stream(self._copy_stream):
+                for s in range(0, B, vb):
+                    for c in range(s, min(s + vb, B), copy_chunk):
+                        e = min(c + copy_chunk, s + vb, B)
+                        dev_imgs[c:e].copy_(hb[c:e], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                    events.append(ev)
+            evals, evecs, info = self.run_device(dev_imgs, events)
+            outs = (self._buf(("h_evals", slot), tuple(evals.shape), torch.float32, pinned=True),
+                    self._buf(("h_evecs", slot), tuple(evecs.shape), torch.float32, pinned=True),
+                    self._buf(("h_info", slot), tuple(info.shape), torch.int32, pinned=True))
+            outs[0].copy_(evals, non_blocking=True)
+            outs[1].copy_(evecs, non_blocking=True)
+            outs[2].copy_(info, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            done[slot] = ev
+            if pending is not None:
+                done[pending[0]].synchronize()
+                yield pending[1]
+            pending = (slot, outs)
+        if pending is not None:
+            done[pending[0]].synchronize()
+            yield pending[1]
+
     @staticmethod
     def launches_per_call(depth: int, which_block: int, n_vit_batches: int) -> int:
         """Kernels libdss_b200 launches for one run_device call (cross-checked against dss_kernel_launch_count)."""
