@@ -14,7 +14,7 @@
 namespace dss {
 
 int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
-int affinity_gemm_tc(const CUtensorMap& tmS, int images, int Nimg, int d, float* Wout, int ldw,
+int affinity_gemm_tc(const CUtensorMap& tmS, const CUtensorMap& tmS_half, int images, int Nimg, int d, float* Wout, int ldw,
                      const unsigned int* img_max, const uint8_t* counts, float lambda, int threshold, cudaStream_t st);
 
 // per-image max |f| (only needed when the features are NOT normalised: they are pre-scaled by a power of two so
@@ -144,10 +144,11 @@ extern "C" int dss_affinity(const float* feats, int B, int N, int d, int flags, 
     rownorm_split_kernel<<<cdiv(rows, 8), 256, 0, st>>>(feats, S, img_max, img_absmax, rows, N, d, dpad, normalize);
     DSS_CHECK_CUDA(cudaGetLastError());
   }
-  CUtensorMap tmS;
+  CUtensorMap tmS, tmS_half;   // A operand: 128-row boxes; B operand: 64-row half boxes (multicast inside the CTA pair)
   int rc = make_tmap_f16(&tmS, S, rows, 3 * dpad, 128);
   if (rc) return rc;
-  return affinity_gemm_tc(tmS, B, N, dpad, Wmat, ldw, img_max, color_counts, color_lambda,
+  if ((rc = make_tmap_f16(&tmS_half, S, rows, 3 * dpad, 64))) return rc;
+  return affinity_gemm_tc(tmS, tmS_half, B, N, dpad, Wmat, ldw, img_max, color_counts, color_lambda,
                           ((flags & DSS_AFF_THRESHOLD_AT_ZERO) ? 1 : 0) | ((flags & DSS_AFF_NO_MAX_SCALE) ? 2 : 0), st);
 }
 

@@ -297,7 +297,7 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
   h->patch_w = reinterpret_cast<__half*>(base + o_patch_w);
   h->patch_b = reinterpret_cast<float*>(base + o_patch_b);
   h->cls = reinterpret_cast<float*>(base + o_cls);
-  if ((rc = make_tmap_f16(&h->tm_patch, h->patch_w, (int)d, (int)Kp, gemm_tile_n((int)d)))) return rc;
+  if ((rc = make_tmap_f16(&h->tm_patch, h->patch_w, (int)d, (int)Kp, gemm_tile_n((int)d) / 2))) return rc;
   h->blocks.resize(c.depth);
   for (int l = 0; l < c.depth; ++l) {
     const dss_vit_block_weights& s = w->blocks[l];
@@ -322,11 +322,11 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
     b.ln2_w = reinterpret_cast<float*>(base + bo[l].ln2_w); b.ln2_b = reinterpret_cast<float*>(base + bo[l].ln2_b);
     b.qkv_b = reinterpret_cast<float*>(base + bo[l].qkv_b); b.proj_b = reinterpret_cast<float*>(base + bo[l].proj_b);
     b.fc1_b = reinterpret_cast<float*>(base + bo[l].fc1_b); b.fc2_b = reinterpret_cast<float*>(base + bo[l].fc2_b);
-    if ((rc = make_tmap_f16(&b.tm_qkv, b.qkv_w, (int)(3 * d), (int)d, gemm_tile_n((int)(3 * d))))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_k, b.qkv_w + d * d, (int)d, (int)d, gemm_tile_n((int)d)))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_proj, b.proj_w, (int)d, (int)d, gemm_tile_n((int)d)))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_fc1, b.fc1_w, (int)hid, (int)d, gemm_tile_n((int)hid)))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_fc2, b.fc2_w, (int)d, (int)hid, gemm_tile_n((int)d)))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_qkv, b.qkv_w, (int)(3 * d), (int)d, gemm_tile_n((int)(3 * d)) / 2))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_k, b.qkv_w + d * d, (int)d, (int)d, gemm_tile_n((int)d) / 2))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_proj, b.proj_w, (int)d, (int)d, gemm_tile_n((int)d) / 2))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_fc1, b.fc1_w, (int)hid, (int)d, gemm_tile_n((int)hid) / 2))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_fc2, b.fc2_w, (int)d, (int)hid, gemm_tile_n((int)d) / 2))) return rc;
   }
   // host copy of the positional grid for interpolation; drop stale interpolations
   const size_t npos = ((size_t)c.grid0 * c.grid0 + 1) * d;
