@@ -86,52 +86,70 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_s);
 
+  // Producer and MMA warps run their loops with ALL lanes on warp-uniform values and let one elected lane issue: the
+  // smem addresses, coordinates and descriptors then live in uniform registers and each UMMA / TMA issue is a couple
+  // of instructions instead of a register-to-uniform "waterfall" loop.
   if (warp == 0) {
-    if (lane == 0) {
+    const uint32_t uQ = __shfl_sync(0xffffffffu, sQ, 0), uK = __shfl_sync(0xffffffffu, sK, 0),
+                   uV = __shfl_sync(0xffffffffu, sV, 0);
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, FA_TILE);
-      tma_load_2d(sQ, &tmQKV, q_full, h * FA_D, row0 + q0);
-      for (int j = 0; j < nt; ++j) {
-        const int s = j % FA_KV_STAGES;
-        const uint32_t ph = (j / FA_KV_STAGES) & 1;
-        mbar_wait(kv_empty(s), ph ^ 1u);
+      tma_load_2d(uQ, &tmQKV, q_full, h * FA_D, row0 + q0);
+    }
+    __syncwarp();
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % FA_KV_STAGES;
+      const uint32_t ph = (j / FA_KV_STAGES) & 1;
+      mbar_wait(kv_empty(s), ph ^ 1u);
+      if (elect_one()) {
         mbar_arrive_expect_tx(kv_full(s), 2 * FA_TILE);
-        tma_load_2d(sK + s * FA_TILE, &tmQKV, kv_full(s), d + h * FA_D, row0 + j * FA_BN);
-        tma_load_2d(sV + s * FA_TILE, &tmQKV, kv_full(s), 2 * d + h * FA_D, row0 + j * FA_BN);
+        tma_load_2d(uK + s * FA_TILE, &tmQKV, kv_full(s), d + h * FA_D, row0 + j * FA_BN);
+        tma_load_2d(uV + s * FA_TILE, &tmQKV, kv_full(s), 2 * d + h * FA_D, row0 + j * FA_BN);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(FA_BM, FA_BN);                 // A, B K-major
-      constexpr uint32_t idesc_pv = umma_idesc_f16(FA_BM, FA_D) | (1u << 16);     // B (= V) MN-major
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int j) {   // S[j & 1] = Q K_j^T
-        const int s = j % FA_KV_STAGES;
-        mbar_wait(kv_full(s), (j / FA_KV_STAGES) & 1);
-        tc_fence_after();
+    constexpr uint32_t idesc_qk = umma_idesc_f16(FA_BM, FA_BN);                 // A, B K-major
+    constexpr uint32_t idesc_pv = umma_idesc_f16(FA_BM, FA_D) | (1u << 16);     // B (= V) MN-major
+    const uint32_t uQ = __shfl_sync(0xffffffffu, sQ, 0), uK = __shfl_sync(0xffffffffu, sK, 0),
+                   uV = __shfl_sync(0xffffffffu, sV, 0), uP = __shfl_sync(0xffffffffu, sP, 0),
+                   utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t qdesc = umma_desc_sw128(uQ);
+    mbar_wait(q_full, 0);
+    auto issue_s = [&](int j) {   // S[j & 1] = Q K_j^T
+      const int s = j % FA_KV_STAGES;
+      mbar_wait(kv_full(s), (j / FA_KV_STAGES) & 1);
+      tc_fence_after();
+      const uint64_t kdesc = umma_desc_sw128(uK + s * FA_TILE);
+      const uint32_t acc = utmem + FA_S_COL + (j & 1) * FA_BN;
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k)
-          umma_f16_ss(tmem_base + FA_S_COL + (j & 1) * FA_BN, umma_desc_sw128(sQ + k * 32),
-                      umma_desc_sw128(sK + s * FA_TILE + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+        for (int k = 0; k < FA_D / 16; ++k)   // +32 B per 16-wide K step = +2 in the descriptor's address field
+          umma_f16_ss(acc, qdesc + 2u * k, kdesc + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
         umma_commit(s_full(j & 1));
-      };
-      issue_s(0);
-      for (int j = 0; j < nt; ++j) {
-        // next score tile first: its S buffer was released by p_full(j-1), observed in the previous iteration
-        if (j + 1 < nt) issue_s(j + 1);
-        // O[j & 1] = P_j V_j once the softmax warps have published P_j (they consumed O_{j-2} before that)
-        mbar_wait(p_full(j & 1), (j >> 1) & 1);
-        tc_fence_after();
-        const int s = j % FA_KV_STAGES;
-        const uint32_t pj = sP + (j & 1) * 2 * FA_TILE;
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int j = 0; j < nt; ++j) {
+      // next score tile first: its S buffer was released by p_full(j-1), observed in the previous iteration
+      if (j + 1 < nt) issue_s(j + 1);
+      // O[j & 1] = P_j V_j once the softmax warps have published P_j (they consumed O_{j-2} before that)
+      mbar_wait(p_full(j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      const int s = j % FA_KV_STAGES;
+      const uint64_t p0 = umma_desc_sw128(uP + (j & 1) * 2 * FA_TILE);              // keys 0..63 (K-major atom)
+      const uint64_t p1 = umma_desc_sw128(uP + (j & 1) * 2 * FA_TILE + FA_TILE);    // keys 64..127
+      const uint64_t vdesc = umma_desc_sw128(uV + s * FA_TILE);                     // +16 key rows = +2048 B = +128
+      const uint32_t acc = utmem + FA_O_COL + (j & 1) * FA_D;
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < FA_BN / 16; ++k) {
-          const uint64_t adesc = umma_desc_sw128(pj + (k >> 2) * FA_TILE + (k & 3) * 32);   // 64-key atoms, K-major
-          const uint64_t bdesc = umma_desc_sw128(sV + s * FA_TILE + k * 16 * 128);          // 16 key rows per step
-          umma_f16_ss(tmem_base + FA_O_COL + (j & 1) * FA_D, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < FA_BN / 16; ++k)
+          umma_f16_ss(acc, (k < 4 ? p0 : p1) + 2u * (k & 3), vdesc + 128u * k, idesc_pv, k != 0 ? 1u : 0u);
         umma_commit(o_full(j & 1));
         umma_commit(kv_empty(s));
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;               // TMEM lane quarter this warp may access
