@@ -134,6 +134,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_
                : "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// 3D tiled store (box depth 1): used for per-image matrices [B, rows, cols] so that rows are clipped per image
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N bulk groups still READ their shared-memory source (the buffers may then be reused)
 template <int N>

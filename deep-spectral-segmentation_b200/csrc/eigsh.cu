@@ -194,23 +194,33 @@ lanczos_laplacian_kernel(EigParams p) {
         // ---- mat-vec  w = S v  (lapnorm)   or   w = (W - D) v  (unnormalised: top of -(D-W))
         for (int i = tid; i < Npad; i += EIG_THREADS) xs[i] = lapn ? dsc[i] * vcur[i] : vcur[i];
         __syncthreads();
-        for (int r = warp * 2; r < N; r += EIG_WARPS * 2) {
-          const bool two = (r + 1) < N;
-          const float4* row0 = reinterpret_cast<const float4*>(W + (size_t)r * ldw);
-          const float4* row1 = reinterpret_cast<const float4*>(W + (size_t)(two ? r + 1 : r) * ldw);
+        // four rows per warp and pass: 4 independent 128-bit loads in flight per lane (the mat-vec is a pure HBM / L2
+        // stream, memory-level parallelism is what sets its bandwidth)
+        for (int r = warp * 4; r < N; r += EIG_WARPS * 4) {
           const float4* x4 = reinterpret_cast<const float4*>(xs);
-          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+          const float4* rowp[4];
+          float acc[4][2];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            rowp[q] = reinterpret_cast<const float4*>(W + (size_t)min(r + q, N - 1) * ldw);
+            acc[q][0] = acc[q][1] = 0.f;
+          }
           for (int i = lane; i < (Npad >> 2); i += 32) {
             const float4 x = x4[i];
-            const float4 u = __ldg(row0 + i);
-            const float4 v = __ldg(row1 + i);
-            a0 = fmaf(u.x, x.x, a0); a1 = fmaf(u.y, x.y, a1); a0 = fmaf(u.z, x.z, a0); a1 = fmaf(u.w, x.w, a1);
-            b0 = fmaf(v.x, x.x, b0); b1 = fmaf(v.y, x.y, b1); b0 = fmaf(v.z, x.z, b0); b1 = fmaf(v.w, x.w, b1);
+            float4 u[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) u[q] = __ldg(rowp[q] + i);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[q][0] = fmaf(u[q].x, x.x, acc[q][0]); acc[q][1] = fmaf(u[q].y, x.y, acc[q][1]);
+              acc[q][0] = fmaf(u[q].z, x.z, acc[q][0]); acc[q][1] = fmaf(u[q].w, x.w, acc[q][1]);
+            }
           }
-          const float sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
-          if (lane == 0) {
-            wv[r] = lapn ? dsc[r] * sa : (plain ? sa : sa - dsc[r] * xs[r]);
-            if (two) wv[r + 1] = lapn ? dsc[r + 1] * sb : (plain ? sb : sb - dsc[r + 1] * xs[r + 1]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float sa = warp_sum(acc[q][0] + acc[q][1]);
+            if (lane == 0 && r + q < N)
+              wv[r + q] = lapn ? dsc[r + q] * sa : (plain ? sa : sa - dsc[r + q] * xs[r + q]);
           }
         }
         __syncthreads();

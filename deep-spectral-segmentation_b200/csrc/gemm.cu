@@ -31,8 +31,10 @@ constexpr int STG_BYTES = BM * STG_LD * 4;
 constexpr int BOX_BYTES = BM * 128;      // TMA-store path staging box: 128 rows x 128 bytes (swizzled)
 
 // epilogues whose output rows are the GEMM rows: written with TMA (the row-remapping ones keep the manual path)
+constexpr int EPI_AFFINITY_F32 = 100;    // internal epilogue id (not in the public enum): batched patch-affinity tile
 __host__ __device__ constexpr bool epi_uses_tma_store(int epi) {
-  return epi == DSS_EPI_BIAS_F16 || epi == DSS_EPI_BIAS_GELU_F16 || epi == DSS_EPI_BIAS_RESID_F32 || epi == DSS_EPI_BIAS_F32;
+  return epi == DSS_EPI_BIAS_F16 || epi == DSS_EPI_BIAS_GELU_F16 || epi == DSS_EPI_BIAS_RESID_F32 ||
+         epi == DSS_EPI_BIAS_F32 || epi == EPI_AFFINITY_F32;
 }
 constexpr int default_stages(int bn, bool tma) { return tma ? (bn == 128 ? 5 : 4) : (bn == 128 ? 4 : 3); }
 // The kernel is L2 -> SM bandwidth bound (~9.6 TB/s measured): a 128 x BN tile needs (128 + BN) * 128 B of operands
@@ -47,8 +49,6 @@ template <int BN, bool TMA_OUT, int ST = default_stages(BN, TMA_OUT)> struct Til
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
 };
 
-// Internal epilogue id (not part of the public enum): batched patch-affinity tile, see affinity.cu
-constexpr int EPI_AFFINITY_F32 = 100;
 
 struct EpiParams {
   void* out;
@@ -99,23 +99,6 @@ __device__ __forceinline__ long long out_row(int m, const EpiParams& p) {
 // Applies the epilogue to 32 consecutive columns [n, n+32) of one row and stores them.
 // ---- coalesced epilogue, second phase: one warp owns one output row of the tile at a time, lane l owns columns
 // n..n+3 (n = n0 + 4*l), so every global access of a warp is one contiguous 512 B (fp32) / 256 B (fp16) segment.
-__device__ __forceinline__ void store_row4_affinity(float4 v, int m, int n, int M, int z, const EpiParams& p) {
-  if (n >= p.ldo) return;
-  const float mx = __uint_as_float(p.img_max[z]);
-  const uint8_t* cnt = p.counts ? p.counts + ((long long)z * M + m) * M + n : nullptr;
-  float w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    float x = w[t];
-    if (p.threshold & 1) x = x > 0.f ? x : 0.f;   // W * (W > 0)
-    if (!(p.threshold & 2)) x = x / mx;           // W / W.max()   (skipped for which_matrix='affinity'/'affinity_svd')
-    if (cnt && n + t < M) x += static_cast<float>(cnt[t]) * p.lambda;   // + W_color * lambda
-    w[t] = (n + t < M) ? x : 0.f;             // row-pitch padding columns are zeros
-  }
-  float* o = reinterpret_cast<float*>(p.out) + ((long long)z * M + m) * p.ldo + n;
-  *reinterpret_cast<float4*>(o) = make_float4(w[0], w[1], w[2], w[3]);
-}
-
 template <int EPI>
 __device__ __forceinline__ void store_row4(float4 v, int m, int n, const EpiParams& p) {
   const long long r = out_row<EPI>(m, p);
@@ -327,6 +310,21 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             x[e] = __uint_as_float(r[e]) + bias_r[e];
             if constexpr (EPI == DSS_EPI_BIAS_GELU_F16) x[e] = gelu_erf(x[e]);
           }
+          if constexpr (EPI == EPI_AFFINITY_F32) {
+            // W[z, m, n] = relu(acc) / max (+ lambda * counts); columns >= M (row-pitch padding) are zeros; rows >= M
+            // are clipped by the per-image (3D) tensor map
+            const int m = tc.m0 + row, n = nc + sl * W;
+            const float mx = __uint_as_float(__ldg(p.img_max + tc.z));
+            const uint8_t* cnt = (p.counts && m < M) ? p.counts + ((long long)tc.z * M + m) * M + n : nullptr;
+#pragma unroll
+            for (int e = 0; e < W; ++e) {
+              float y = x[e];
+              if (p.threshold & 1) y = y > 0.f ? y : 0.f;   // W * (W > 0)
+              if (!(p.threshold & 2)) y = y / mx;           // W / W.max()
+              if (cnt && n + e < M) y += static_cast<float>(cnt[e]) * p.lambda;   // + W_color * lambda
+              x[e] = (n + e < M) ? y : 0.f;
+            }
+          }
           // the staging box is free once the store issued two boxes ago has finished READING it
           if (issuer) tma_store_wait_read<1>();
           asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
@@ -353,6 +351,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             if (live) {
               if constexpr (EPI == DSS_EPI_BIAS_RESID_F32)
                 tma_reduce_add_2d(&tmC, sbuf, nc, tc.m0);
+              else if constexpr (EPI == EPI_AFFINITY_F32)
+                tma_store_3d(&tmC, sbuf, nc, tc.m0, tc.z);
               else
                 tma_store_2d(&tmC, sbuf, nc, tc.m0);
             }
@@ -425,10 +425,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             if (m >= M) continue;
             float4 x = v[i];
             x.x += y[i].x; x.y += y[i].y; x.z += y[i].z; x.w += y[i].w;
-            if constexpr (EPI == EPI_AFFINITY_F32)
-              store_row4_affinity(x, m, nc + cl, M, tc.z, p);
-            else
-              store_row4<EPI>(x, m, nc + cl, p);
+            store_row4<EPI>(x, m, nc + cl, p);
           }
         }
       }
@@ -533,6 +530,25 @@ int make_tmap_out(CUtensorMap* tm, const void* ptr, int rows, int cols, int is_f
   return DSS_OK;
 }
 
+// Per-image fp32 output [images, rows, ld] for the affinity epilogue: 3D map, box 32 columns x 128 rows x 1 image
+int make_tmap_out3d_f32(CUtensorMap* tm, const void* ptr, int images, int rows, int ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return DSS_ERR_CUDA;
+  DSS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0, "affinity output must be 16-byte aligned / pitched");
+  cuuint64_t gdim[3] = {(cuuint64_t)ld, (cuuint64_t)rows, (cuuint64_t)images};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, (cuuint64_t)rows * ld * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3D output) failed with CUresult %d", (int)r);
+    return DSS_ERR_CUDA;
+  }
+  return DSS_OK;
+}
+
 template <int EPI, int BN, int ST = default_stages(BN, epi_uses_tma_store(EPI))>
 static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, int M, int N, int K,
                         const EpiParams& p, cudaStream_t st, int kclass, int batch) {
@@ -620,7 +636,10 @@ int affinity_gemm_tc(const CUtensorMap& tmS, const CUtensorMap& tmS_half, int im
                      cudaStream_t st) {
   EpiParams p{Wout, nullptr, nullptr, ldw, 0, 0, Nimg, img_max, counts, lambda, threshold, d / BK};
   DSS_REQUIRE(d % BK == 0, "affinity: feature dim must be a multiple of %d for the tensor-core path (got %d)", BK, d);
-  return launch_tc<EPI_AFFINITY_F32>(tmS, tmS_half, nullptr, Nimg, ldw, 3 * d, p, st, KC_AFFINITY, 128, images);
+  CUtensorMap tmW;
+  int rc = make_tmap_out3d_f32(&tmW, Wout, images, Nimg, ldw);
+  if (rc) return rc;
+  return launch_tc<EPI_AFFINITY_F32>(tmS, tmS_half, &tmW, Nimg, ldw, 3 * d, p, st, KC_AFFINITY, 128, images);
 }
 
 template <int EPI>
