@@ -345,7 +345,9 @@ def run_ours(args, rank, local_rank, world):
     if dom:
         traffic = None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed ncu capture
-            traffic = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text()).get(dom["kernel"])
+            per_img = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())["per_image_bytes"].get(dom["kernel"])
+            imgs_per_launch = B if dom["kernel"] in ("eigsh", "affinity", "rownorm") else args.vit_batch
+            traffic = per_img * imgs_per_launch if per_img else None
         except Exception:
             pass
         roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],

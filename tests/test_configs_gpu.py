@@ -71,3 +71,20 @@ def test_config2_shape_batch_properties(cuda):
     perm = torch.randperm(24, generator=torch.Generator().manual_seed(0))
     ev2, vec2, _ = pipe.run_host(imgs[perm].contiguous().pin_memory())
     assert torch.equal(vec2, vec[perm]) and torch.equal(ev2, ev[perm])
+
+
+def test_config5_vitb8_640_K32_properties(cuda):
+    """BASELINE config 5 shape: dino_vitb8 at 640x640 (6400 patches, T = 6401), K = 32."""
+    vit = load_pkg("vit")
+    spectral = load_pkg("spectral")
+    synth = load_pkg("synth")
+    model, _, P, _ = vit.get_model("dino_vitb8", seed=0, device=cuda)
+    imgs = synth.blobs_batch(1, 640, 640, seed0=3)
+    k = model.forward_k(imgs.to(cuda))
+    assert tuple(k.shape) == (1, 6400, 768) and torch.isfinite(k).all()
+    Wm = spectral.affinity(k)
+    ev, vec, info, resid = spectral.eigsh_laplacian(Wm, 6400, 32)
+    torch.cuda.synchronize()
+    print(f"C5: lanczos steps {int(info[0, 0])}, converged {int(info[0, 1])}, eigenvalues {ev[0, :6].tolist()}")
+    assert int(info[0, 1]) == 1
+    _props(ev[0], vec[0], Wm[0], 6400)
