@@ -49,12 +49,15 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING a timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions. The sampler process is started before
+    the warm-up (it needs a few hundred ms to come up); only samples whose timestamp falls inside a timed window
+    (mark_begin / mark_end) are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.proc, self.path, self.windows, self._t0 = index, None, None, [], None
 
     def start(self):
         try:
@@ -66,32 +69,45 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self._t0 = time.time()
+
+    def mark_end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, time.time()))
+            self._t0 = None
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in Path(self.path).read_text().splitlines():
                 p = [x.strip() for x in line.split(",")]
-                if len(p) < 7:
+                if len(p) < 8:
                     continue
-                sm.append(float(p[0])); mx = float(p[1])
-                for n, v in zip(names, p[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                try:
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except Exception:
+                    ts = None
+                rows.append((ts, float(p[1]), float(p[2]), [n for n, v in zip(names, p[4:8]) if v.lower().startswith("active")]))
             os.unlink(self.path)
         except Exception:
             pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [r for r in rows if r[0] is not None and any(a - 0.02 <= r[0] <= b + 0.02 for a, b in self.windows)]
+        used, where = (inside, "timed regions") if inside else (rows, "whole run (no sample fell inside the timed regions)")
+        sm = sorted(r[1] for r in used)
+        reasons = sorted({n for r in used for n in r[3]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": used[-1][2] if used else None,
+                "reasons": reasons, "samples": len(used), "window": where}
 
 
 def load_peaks():
@@ -258,23 +274,24 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     # ---- device-resident throughput
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         pipe.run_device(dev_imgs)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     info = None
     for _ in range(args.steps):
         _, _, info = pipe.run_device(dev_imgs)
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - n0
-    clocks = sampler.stop()
     value = world * B * args.steps / (ms * 1e-3)
     conv = int(info[:, 1].sum().item())
     steps_mean = float(info[:, 0].float().mean().item())
@@ -284,12 +301,15 @@ def run_ours(args, rank, local_rank, world):
     for _ in pipe.run_host_pipelined([host_imgs] * 2):
         pass
     barrier()
+    sampler.mark_begin()
     e0.record()
     out = None
     for out in pipe.run_host_pipelined([host_imgs] * args.steps):
         pass
     e1.record()
     barrier()
+    sampler.mark_end()
+    clocks = sampler.stop()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     h2d = int(host_imgs.numel())
