@@ -220,6 +220,41 @@ def extract_eigs(images_root: str, features_dir: str, output_dir: str, which_mat
     print(f"Finished in {time.time() - start:.1f}s")
 
 
+def _extract_single_region_segmentations(inp, threshold: float, output_dir: str):
+    """Worker with the reference's signature (extract.py:364-390): eigenvector 1 > threshold on the patch grid -> PNG."""
+    from PIL import Image
+    index, (feature_path, eigs_path) = inp
+    data_dict = torch.load(feature_path, map_location="cpu")
+    data_dict.update(torch.load(eigs_path, map_location="cpu", weights_only=False))
+    id = Path(data_dict["id"])
+    output_file = str(Path(output_dir) / f"{id}.png")
+    if Path(output_file).is_file():
+        print(f"Skipping existing file {str(output_file)}")
+        return
+    B, C, H, W, P, H_patch, W_patch, H_pad, W_pad = utils.get_image_sizes(data_dict)
+    eigenvector = data_dict["eigenvectors"][1].numpy()  # smallest non-zero eigenvector
+    segmap = (eigenvector > threshold).reshape(H_patch, W_patch)
+    Image.fromarray(segmap).convert("L").save(output_file)
+
+
+def extract_single_region_segmentations(features_dir: str, eigs_dir: str, output_dir: str, threshold: float = 0.0,
+                                        multiprocessing: int = 0, yes: Optional[bool] = None):
+    """
+    First consumer of the eigs files, same command / file contract as the reference
+    (extract/extract.py:393-411): thresholds the Fiedler-like eigenvector of every image into a patch-grid mask.
+
+    Example:
+    python extract.py extract_single_region_segmentations \
+        --features_dir "./data/VOC2012/features/dino_vits16" \
+        --eigs_dir "./data/VOC2012/eigs/laplacian" \
+        --output_dir "./data/VOC2012/single_region_segmentation/patches" \
+    """
+    utils.make_output_dir(output_dir, assume_yes=yes)
+    inputs = utils.get_paired_input_files(features_dir, eigs_dir)
+    utils.parallel_process(inputs, lambda inp: _extract_single_region_segmentations(inp, threshold, output_dir),
+                           multiprocessing)
+
+
 def extract_all(images_list: str, images_root: Optional[str], model_name: str, features_dir: Optional[str],
                 eigs_dir: str, K: int = 20, batch_size: int = 16, which_block: int = -1, normalize: bool = True,
                 threshold_at_zero: bool = True, lapnorm: bool = True, image_color_lambda: float = 0.0,

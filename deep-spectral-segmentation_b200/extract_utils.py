@@ -60,6 +60,23 @@ def get_image_sizes(data_dict: dict, downsample_factor: Optional[int] = None):
     return (B, C, H, W, P, H_patch, W_patch, H_pad, W_pad)
 
 
+def _get_files(p: str):
+    if Path(p).is_dir():
+        return sorted(Path(p).iterdir())
+    elif Path(p).is_file():
+        return Path(p).read_text().splitlines()
+    else:
+        raise ValueError(p)
+
+
+def get_paired_input_files(path1: str, path2: str):
+    """extract_utils.py:82-95: pairs the sorted entries of two directories (or list files)."""
+    files1 = _get_files(path1)
+    files2 = _get_files(path2)
+    assert len(files1) == len(files2)
+    return list(enumerate(zip(files1, files2)))
+
+
 def make_output_dir(output_dir, check_if_empty=True, assume_yes: Optional[bool] = None):
     """Creates the directory; like the reference it asks before writing into a non-empty one. When stdin is not a
     terminal (batch jobs, tests) or assume_yes is set, it continues without blocking (skip-if-exists makes that safe)."""

@@ -17,5 +17,6 @@ if __name__ == "__main__":
     _cli.Fire(dict(
         extract_features=_extract.extract_features,
         extract_eigs=_extract.extract_eigs,
+        extract_single_region_segmentations=_extract.extract_single_region_segmentations,
         extract_all=_extract.extract_all,
     ))

@@ -124,3 +124,35 @@ def test_synthetic_inputs_are_seeded():
     assert shapes == synth.voc_shapes(1000, 0) and max(max(s) for s in shapes) == 500
     f = synth.structured_features(100, 32, 4, 1)
     assert torch.equal(f, synth.structured_features(100, 32, 4, 1)) and f.dtype == torch.float32
+
+
+def test_single_region_segmentation_matches_reference(tmp_path):
+    """the first consumer of eigs/*.pth. Bit-exact PNG against the reference's own function when
+    the reference is present; always against the restated rule (eigenvector 1 > threshold on the patch grid)."""
+    from PIL import Image
+    from oracle import ref_shim
+    ex = load_pkg("extract")
+    fdir, edir = tmp_path / "features", tmp_path / "eigs"
+    fdir.mkdir(); edir.mkdir()
+    g = torch.Generator().manual_seed(0)
+    for i, (H, W) in enumerate([(100, 132), (96, 96)]):
+        Hp, Wp = H // 16, W // 16
+        name = f"im{i}"
+        torch.save(ex._feature_dict(torch.randn(1, Hp * Wp, 8, generator=g), i, f"{name}.jpg", "dino_vits16", 16, H, W),
+                   fdir / f"{name}.pth")
+        torch.save({"eigenvalues": torch.rand(3), "eigenvectors": torch.randn(3, Hp * Wp, generator=g)}, edir / f"{name}.pth")
+    out = tmp_path / "seg"
+    ex.extract_single_region_segmentations(str(fdir), str(edir), str(out), threshold=0.1)
+    for i, (H, W) in enumerate([(100, 132), (96, 96)]):
+        seg = np.array(Image.open(out / f"im{i}.png"))
+        ev = torch.load(edir / f"im{i}.pth")["eigenvectors"][1].numpy()
+        assert seg.shape == (H // 16, W // 16) and seg.dtype == np.uint8
+        assert np.array_equal(seg, ((ev > 0.1).reshape(H // 16, W // 16) * 255).astype(np.uint8))
+    if ref_shim.available():
+        ref = ref_shim.load_reference()
+        ref_out = tmp_path / "seg_ref"
+        ref_out.mkdir()
+        for inp in ref.utils.get_paired_input_files(str(fdir), str(edir)):
+            ref._extract_single_region_segmentations(inp, threshold=0.1, output_dir=str(ref_out))
+        for f in sorted(out.iterdir()):
+            assert (ref_out / f.name).read_bytes() == f.read_bytes()      # byte-identical PNG files
