@@ -21,8 +21,12 @@
 
 namespace dss {
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;   // BK: one 128-byte swizzle atom of fp16 (one TMA box / 4 UMMAs)
+constexpr int A_ATOM_BYTES = BM * BK * 2;
+// swizzle atoms (64-deep K slabs) per pipeline stage. 128-wide tiles: 2 (128-deep stages halve the MMA warp's
+// per-FLOP wait/elect/commit overhead: +12 % measured); 256-wide tiles: 1 (their UMMAs are already twice as long and
+// only 2 x 96 KB stages would fit, which hides less load latency than 4 x 48 KB: 790 vs 828 TFLOP/s measured).
+constexpr int slabs_per_stage(int bn) { return bn == 128 ? 2 : 1; }
 constexpr int EPI_WARPS = 16;            // 4 TMEM lane quarters x 4 column slices
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int MANUAL_EPI_WARPS = 8;      // the row-remapping / affinity epilogues use the first 8 epilogue warps
@@ -36,12 +40,15 @@ __host__ __device__ constexpr bool epi_uses_tma_store(int epi) {
   return epi == DSS_EPI_BIAS_F16 || epi == DSS_EPI_BIAS_GELU_F16 || epi == DSS_EPI_BIAS_RESID_F32 ||
          epi == DSS_EPI_BIAS_F32 || epi == EPI_AFFINITY_F32;
 }
-constexpr int default_stages(int bn, bool tma) { return tma ? (bn == 128 ? 5 : 4) : (bn == 128 ? 4 : 3); }
+constexpr int default_stages(int bn, bool tma) { return tma ? (bn == 128 ? 3 : 4) : 2; }
 // The kernel is L2 -> SM bandwidth bound (~9.6 TB/s measured): a 128 x BN tile needs (128 + BN) * 128 B of operands
 // per 64-deep K slab, so wide tiles and a deep ring (bytes in flight) are what matter.
 template <int BN, bool TMA_OUT, int ST = default_stages(BN, TMA_OUT)> struct TileCfg {
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int KS = slabs_per_stage(BN);
+  static constexpr int A_TILE_BYTES = KS * A_ATOM_BYTES;
+  static constexpr int B_ATOM_BYTES = BN * BK * 2;
+  static constexpr int B_TILE_BYTES = KS * B_ATOM_BYTES;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;   // [A atom 0 | A atom 1 | B atom 0 | B atom 1]
   static constexpr int STAGES = ST;
   static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;   // two fp32 accumulators, power-of-two allocation
   static constexpr int STAGING_BYTES = TMA_OUT ? 2 * BOX_BYTES : 4 * STG_BYTES;
@@ -150,6 +157,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         int total_items, EpiParams p) {
   using Cfg = TileCfg<BN, epi_uses_tma_store(EPI), ST>;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, TMEM_COLS = Cfg::TMEM_COLS;
+  constexpr int KS = Cfg::KS, A_TILE_BYTES = Cfg::A_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment (the swizzle pattern is a function of address bits [7,10))
   const uint32_t raw = smem_u32(smem_raw);
@@ -168,7 +176,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = (K + BK - 1) / BK;
+  const int num_kb = (K + KS * BK - 1) / (KS * BK);   // pipeline stages per tile (128-deep)
   const int rank = (int)cluster_ctarank();          // 0 / 1 inside the CTA pair
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
@@ -200,29 +208,37 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     // The whole warp runs the loop with warp-uniform values (so addresses / coordinates stay in uniform registers and
     // the TMA issue needs no register-to-uniform "waterfall"); one elected lane issues.
     const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0);
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;   // ring position, carried across tiles (no division in the loop)
     for (int t = cid; t < total_items; t += ncl) {
       const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank);
       const int row_base = tc.z * p.batch_rows;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(bar_base + 8u * (STAGES + s), ph ^ 1u);
         const uint32_t sa = ubase + s * STAGE_BYTES;
         const uint32_t fb = bar_base + 8u * s;
-        // split-fp16 Gram product: A = [hi | hi/64 | 64 lo], B = [hi | 64 lo | hi/64] are the same array read
-        // with the last two groups of K slabs swapped
-        int kbB = kb;
-        if (p.perm_blocks > 0 && kb >= p.perm_blocks)
-          kbB = kb < 2 * p.perm_blocks ? kb + p.perm_blocks : kb - p.perm_blocks;
+        int ka[KS], kbB[KS];
+#pragma unroll
+        for (int a = 0; a < KS; ++a) {
+          ka[a] = kb * KS + a;   // 64-deep slab index
+          // split-fp16 Gram product: A = [hi | hi/64 | 64 lo], B = [hi | 64 lo | hi/64] are the same array read
+          // with the last two groups of K slabs swapped
+          kbB[a] = ka[a];
+          if (p.perm_blocks > 0 && ka[a] >= p.perm_blocks && ka[a] < 3 * p.perm_blocks)
+            kbB[a] = ka[a] < 2 * p.perm_blocks ? ka[a] + p.perm_blocks : ka[a] - p.perm_blocks;
+        }
         if (elect_one()) {
           mbar_arrive_expect_tx(fb, STAGE_BYTES);
-          tma_load_2d(sa, &tmA, fb, kb * BK, row_base + tc.m0);
-          // this CTA's half of the weight tile (box 64 x BN/2 rows), delivered to both CTAs of the pair
-          tma_load_2d_mc(sa + A_TILE_BYTES + rank * (Cfg::B_TILE_BYTES / 2), &tmB, fb, kbB * BK,
-                         row_base + tc.n0 + rank * (BN / 2), (uint16_t)0x3);
+#pragma unroll
+          for (int a = 0; a < KS; ++a) {
+            tma_load_2d(sa + a * A_ATOM_BYTES, &tmA, fb, ka[a] * BK, row_base + tc.m0);
+            // this CTA's half of the weight slab (box 64 x BN/2 rows), delivered to both CTAs of the pair
+            tma_load_2d_mc(sa + A_TILE_BYTES + a * Cfg::B_ATOM_BYTES + rank * (Cfg::B_ATOM_BYTES / 2), &tmB, fb,
+                           kbB[a] * BK, row_base + tc.n0 + rank * (BN / 2), (uint16_t)0x3);
+          }
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -231,30 +247,34 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
     const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0);
     const uint32_t utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
-    int it = 0, lt = 0;
+    int s = 0, lt = 0;
+    uint32_t ph = 0;
     for (int t = cid; t < total_items; t += ncl, ++lt) {
       const int buf = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       mbar_wait(tempty_bar(buf), aph ^ 1u);  // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t acc = utmem + buf * BN;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(bar_base + 8u * s, ph);
         tc_fence_after();
         const uint32_t sa = ubase + s * STAGE_BYTES;
-        // advancing K inside the 128 B swizzle atom = advancing the descriptor's start-address field by 32 B >> 4
+        // advancing K inside a 128 B swizzle atom = advancing the descriptor's start-address field by 32 B >> 4;
+        // the second atom of the stage starts A_ATOM_BYTES / B_ATOM_BYTES further
         const uint64_t adesc = umma_desc_sw128(sa);
         const uint64_t bdesc = umma_desc_sw128(sa + A_TILE_BYTES);
         const uint32_t eb = bar_base + 8u * (STAGES + s);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_f16_ss(acc, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int a = 0; a < KS; ++a)
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16_ss(acc, adesc + (uint64_t)(a * (A_ATOM_BYTES >> 4) + 2 * k),
+                          bdesc + (uint64_t)(a * (Cfg::B_ATOM_BYTES >> 4) + 2 * k), idesc, (kb | a | k) != 0 ? 1u : 0u);
           umma_commit_mc(eb, (uint16_t)0x3);  // slot free (in this CTA) once these MMAs have consumed it
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
       if (elect_one()) umma_commit(tfull_bar(buf));  // accumulator complete
       __syncwarp();
@@ -593,7 +613,9 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      const EpiParams& p, cudaStream_t st, int kclass, int bn, int batch = 1) {
   switch (bn) {
     case 128: return launch_tc_bn<EPI, 128>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
-    case 256: return launch_tc_bn<EPI, 256>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
+    case 256:
+      if constexpr (epi_uses_tma_store(EPI)) return launch_tc_bn<EPI, 256>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
+      break;
   }
   set_error("gemm: unsupported tile width %d", bn);
   return DSS_ERR_BAD_ARG;
@@ -663,7 +685,7 @@ extern "C" int dss_op_gemm_f16(const void* A, const void* Wt, const float* bias,
   if (rc) return rc;
   DSS_REQUIRE(A && Wt, "gemm: null operand");
   CUtensorMap tmA, tmB;
-  const int bn = gemm_tile_n(N);
+  const int bn = epi_uses_tma_store(epilogue) ? gemm_tile_n(N) : 128;   // row-remapping epilogues: 128-wide only
   if ((rc = make_tmap_f16(&tmA, A, M, K, BM))) return rc;
   if ((rc = make_tmap_f16(&tmB, Wt, N, K, bn / 2))) return rc;   // each CTA of a pair loads (and multicasts) half a tile
   CUtensorMap tmC;
@@ -708,9 +730,8 @@ extern "C" int dss_debug_gemm_cfg(const void* A, const void* Wt, const float* bi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int key = bn * 10 + stages;
   switch (key) {
+    case 1282: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 2>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
     case 1283: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 3>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
-    case 1284: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 4>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
-    case 1285: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 5>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
     case 2563: return launch_tc_bn<DSS_EPI_BIAS_F16, 256, 3>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
     case 2564: return launch_tc_bn<DSS_EPI_BIAS_F16, 256, 4>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
   }

@@ -192,7 +192,7 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
   // tokens: x[b, 1+n, :] = patch_embed + pos ; x[b, 0, :] = cls + pos[0]
   if ((rc = launch_im2col(img, w.patches, B, H, W, P, st))) return rc;
   if ((rc = gemm_f16_tc(tm_patches, h->tm_patch, nullptr, h->patch_b, w.x, B * Np, d, Kp, DSS_EPI_PATCH_F32, pos, Np, T, st,
-                        KC_GEMM_PATCH, gemm_tile_n(d))))
+                        KC_GEMM_PATCH, 128)))
     return rc;
   if ((rc = launch_cls_row(w.x, h->cls, pos, B, T, d, st))) return rc;
 
@@ -219,7 +219,7 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
     if ((rc = launch_layernorm(w.x, bw.ln1_w, bw.ln1_b, w.xn, M, d, c.ln_eps, st))) return rc;
     // K third of the qkv projection (weight rows [d, 2d)), CLS rows dropped: out[b, n, :] == qkv[b, 1+n, d:2d]
     if ((rc = gemm_f16_tc(tm_xn, bw.tm_k, nullptr, bw.qkv_b + d, out, M, d, d, DSS_EPI_DROPCLS_F32, nullptr, T, Np, st,
-                          KC_GEMM_KPROJ, gemm_tile_n(d))))
+                          KC_GEMM_KPROJ, 128)))
       return rc;
   } else {
     DSS_CHECK_CUDA(cudaMemcpyAsync(out, w.x, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -297,7 +297,7 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
   h->patch_w = reinterpret_cast<__half*>(base + o_patch_w);
   h->patch_b = reinterpret_cast<float*>(base + o_patch_b);
   h->cls = reinterpret_cast<float*>(base + o_cls);
-  if ((rc = make_tmap_f16(&h->tm_patch, h->patch_w, (int)d, (int)Kp, gemm_tile_n((int)d) / 2))) return rc;
+  if ((rc = make_tmap_f16(&h->tm_patch, h->patch_w, (int)d, (int)Kp, 128 / 2))) return rc;
   h->blocks.resize(c.depth);
   for (int l = 0; l < c.depth; ++l) {
     const dss_vit_block_weights& s = w->blocks[l];
@@ -323,7 +323,7 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
     b.qkv_b = reinterpret_cast<float*>(base + bo[l].qkv_b); b.proj_b = reinterpret_cast<float*>(base + bo[l].proj_b);
     b.fc1_b = reinterpret_cast<float*>(base + bo[l].fc1_b); b.fc2_b = reinterpret_cast<float*>(base + bo[l].fc2_b);
     if ((rc = make_tmap_f16(&b.tm_qkv, b.qkv_w, (int)(3 * d), (int)d, gemm_tile_n((int)(3 * d)) / 2))) return rc;
-    if ((rc = make_tmap_f16(&b.tm_k, b.qkv_w + d * d, (int)d, (int)d, gemm_tile_n((int)d) / 2))) return rc;
+    if ((rc = make_tmap_f16(&b.tm_k, b.qkv_w + d * d, (int)d, (int)d, 128 / 2))) return rc;
     if ((rc = make_tmap_f16(&b.tm_proj, b.proj_w, (int)d, (int)d, gemm_tile_n((int)d) / 2))) return rc;
     if ((rc = make_tmap_f16(&b.tm_fc1, b.fc1_w, (int)hid, (int)d, gemm_tile_n((int)hid) / 2))) return rc;
     if ((rc = make_tmap_f16(&b.tm_fc2, b.fc2_w, (int)d, (int)hid, gemm_tile_n((int)d) / 2))) return rc;
