@@ -97,7 +97,8 @@ def test_layernorm(cuda, d):
 
 
 @pytest.mark.parametrize("impl", ["dss_op_attention_tc_f16", "dss_op_attention_f16"])
-@pytest.mark.parametrize("B,T,heads", [(1, 64, 6), (2, 197, 6), (2, 901, 6), (1, 130, 12), (3, 257, 6)])
+@pytest.mark.parametrize("B,T,heads", [(1, 64, 6), (2, 197, 6), (2, 901, 6), (1, 130, 12), (3, 257, 6), (4, 577, 6),
+                                       (40, 901, 6), (30, 257, 6), (70, 100, 6)])
 def test_attention(cuda, B, T, heads, impl):
     _lib = load_pkg("_lib"); lib = _lib.load()
     g = torch.Generator(device="cuda").manual_seed(T)
