@@ -23,6 +23,8 @@
 // by the MUFU pipe (128 x 128 exp2 per tile at 16 per clock per SM), not by the tensor pipe.
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace dss {
@@ -43,8 +45,9 @@ constexpr int FA_KV_STAGES = 3;
 constexpr int FA_SMEM = FA_TILE * (4 + 2 * FA_KV_STAGES + 4);
 constexpr int FA_TMEM_COLS = 512;
 constexpr int FA_S_COL = 0, FA_O_COL = 256;   // S_A, S_B at columns 0 / 128; O_g[i] at 256 + 128 g + 64 i
-constexpr int FA_NBARS = 8 + 2 * FA_KV_STAGES + 8;
+constexpr int FA_NBARS = 8 + 2 * FA_KV_STAGES + 10;
 
+// 10 warps = 3 on some SM sub-partitions: 16 K registers / (3 x 32 threads) caps the kernel at 168 registers
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int heads,
                          int nq2, int total_items) {
@@ -63,6 +66,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
   auto s_full = [&](int g) { return bar0 + 8u * (8 + 2 * FA_KV_STAGES + g); };
   auto p_full = [&](int g) { return bar0 + 8u * (10 + 2 * FA_KV_STAGES + g); };
   auto o_full = [&](int g, int i) { return bar0 + 8u * (12 + 2 * FA_KV_STAGES + g * 2 + i); };
+  auto s_free = [&](int g) { return bar0 + 8u * (16 + 2 * FA_KV_STAGES + g); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = heads * FA_D;
@@ -83,6 +87,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full(g), 1);
       mbar_init(p_full(g), 128);
+      mbar_init(s_free(g), 128);
     }
     mbar_fence_init();
   }
@@ -138,62 +143,68 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
     const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
     const int m_total = my_items * nt;   // key-tile steps of this CTA, over all of its items
-    // cursor of the next score tile to issue (same position for both query tiles; advanced after B's)
-    int sj = 0, sq = 0, ss = 0;
-    uint32_t sph = 0;
-    auto issue_s = [&](int g) {   // S_g = Q_g K_j^T
-      if (sj == 0) mbar_wait(q_full(g, sq & 1), (sq >> 1) & 1);
-      mbar_wait(kv_full(ss), sph);
-      tc_fence_after();
-      const uint64_t qdesc = umma_desc_sw128(uQ + (g * 2 + (sq & 1)) * FA_TILE);
-      const uint64_t kdesc = umma_desc_sw128(uK + ss * FA_TILE);
-      const int kc = sj == nt - 1 ? kc_last : FA_BN;
-      const uint32_t idesc = idesc_qk0 | (static_cast<uint32_t>(kc >> 3) << 17);
-      const uint32_t acc = utmem + FA_S_COL + g * FA_BN;
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k)   // +32 B per 16-wide K step = +2 in the descriptor's address field
-          umma_f16_ss(acc, qdesc + 2u * k, kdesc + 2u * k, idesc, k != 0 ? 1u : 0u);
-        umma_commit(s_full(g));
-        if (sj == nt - 1) umma_commit(q_empty(g, sq & 1));   // last score tile of the item: Q_g may be replaced
-      }
-      __syncwarp();
-    };
-    auto advance_s = [&]() {
-      if (++sj == nt) { sj = 0; ++sq; }
-      if (++ss == FA_KV_STAGES) { ss = 0; sph ^= 1u; }
-    };
-    if (m_total > 0) {
-      issue_s(0);
-      issue_s(1);
-      advance_s();
-    }
-    int pj = 0, ps = 0;
-    for (int m = 0; m < m_total; ++m) {
-      const int ksteps = (pj == nt - 1 ? kc_last : FA_BN) >> 4;
-      const uint64_t vdesc = umma_desc_sw128(uV + ps * FA_TILE);   // +16 key rows = +2048 B = +128
+    // Event loop: each query tile g has a cursor for its next score tile (needs S_g released by the softmax warps)
+    // and one for its next P V product (needs P_g published); whichever is ready is issued.
+    int ns[2] = {0, 0}, sj[2] = {0, 0}, sq[2] = {0, 0}, ss[2] = {0, 0};     // score cursor: step, key tile, item, ring stage
+    uint32_t sph[2] = {0, 0};
+    int np[2] = {0, 0}, pj[2] = {0, 0}, ps[2] = {0, 0};                      // P V cursor
+    uint32_t idle = 0;
+    while (np[0] < m_total || np[1] < m_total) {
+      bool progress = false;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        // the softmax warps of tile g have read S_g(m) and published P_g(m) (and consumed O_g(m-2) before that)
-        mbar_wait(p_full(g), m & 1);
-        tc_fence_after();
-        if (m + 1 < m_total) issue_s(g);   // next score tile first: the softmax warps wait for it next
-        const uint64_t p0 = umma_desc_sw128(uP + g * 2 * FA_TILE);              // keys 0..63 (K-major atom)
-        const uint64_t p1 = umma_desc_sw128(uP + g * 2 * FA_TILE + FA_TILE);    // keys 64..127
-        const uint32_t acc = utmem + FA_O_COL + g * 2 * FA_D + (m & 1) * FA_D;
-        if (elect_one()) {
+        // ---- S_g(n) = Q_g K_j^T: S_g is free once the softmax warps have read S_g(n-1) for the last time
+        // (all probes are non-blocking: a blocking wait for K_j here could starve the other query tile's P V product,
+        // which is what releases the ring slot K_j is waiting for)
+        if (ns[g] < m_total && (ns[g] == 0 || mbar_test_all(s_free(g), (ns[g] - 1) & 1)) &&
+            mbar_test_all(kv_full(ss[g]), sph[g]) &&
+            (sj[g] != 0 || mbar_test_all(q_full(g, sq[g] & 1), (sq[g] >> 1) & 1))) {
+          tc_fence_after();
+          const uint64_t qdesc = umma_desc_sw128(uQ + (g * 2 + (sq[g] & 1)) * FA_TILE);
+          const uint64_t kdesc = umma_desc_sw128(uK + ss[g] * FA_TILE);
+          const int kc = sj[g] == nt - 1 ? kc_last : FA_BN;
+          const uint32_t idesc = idesc_qk0 | (static_cast<uint32_t>(kc >> 3) << 17);
+          const uint32_t acc = utmem + FA_S_COL + g * FA_BN;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < FA_BN / 16; ++k)
-            if (k < ksteps)
-              umma_f16_ss(acc, (k < 4 ? p0 : p1) + 2u * (k & 3), vdesc + 128u * k, idesc_pv, k != 0 ? 1u : 0u);
-          umma_commit(o_full(g, m & 1));
-          if (g == 1) umma_commit(kv_empty(ps));   // both query tiles are done with K_j / V_j
+            for (int k = 0; k < FA_D / 16; ++k)   // +32 B per 16-wide K step = +2 in the descriptor's address field
+              umma_f16_ss(acc, qdesc + 2u * k, kdesc + 2u * k, idesc, k != 0 ? 1u : 0u);
+            umma_commit(s_full(g));
+            if (sj[g] == nt - 1) umma_commit(q_empty(g, sq[g] & 1));   // last score tile of the item: Q_g may be replaced
+          }
+          __syncwarp();
+          ++ns[g];
+          if (++sj[g] == nt) { sj[g] = 0; ++sq[g]; }
+          if (++ss[g] == FA_KV_STAGES) { ss[g] = 0; sph[g] ^= 1u; }
+          progress = true;
         }
-        __syncwarp();
+        // ---- O_g[n & 1] = P_g V_j once the softmax warps have published P_g(n) (they consumed O_g(n-2) before that)
+        if (np[g] < m_total && mbar_test_all(p_full(g), np[g] & 1)) {
+          tc_fence_after();
+          const int n = np[g];
+          const int ksteps = (pj[g] == nt - 1 ? kc_last : FA_BN) >> 4;
+          const uint64_t vdesc = umma_desc_sw128(uV + ps[g] * FA_TILE);   // +16 key rows = +2048 B = +128
+          const uint64_t p0 = umma_desc_sw128(uP + g * 2 * FA_TILE);              // keys 0..63 (K-major atom)
+          const uint64_t p1 = umma_desc_sw128(uP + g * 2 * FA_TILE + FA_TILE);    // keys 64..127
+          const uint32_t acc = utmem + FA_O_COL + g * 2 * FA_D + (n & 1) * FA_D;
+          const bool release = np[g ^ 1] > n;   // the other query tile has already issued its P V_j: K_j / V_j are done
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < FA_BN / 16; ++k)
+              if (k < ksteps)
+                umma_f16_ss(acc, (k < 4 ? p0 : p1) + 2u * (k & 3), vdesc + 128u * k, idesc_pv, k != 0 ? 1u : 0u);
+            umma_commit(o_full(g, n & 1));
+            if (release) umma_commit(kv_empty(ps[g]));
+          }
+          __syncwarp();
+          ++np[g];
+          if (++pj[g] == nt) pj[g] = 0;
+          if (++ps[g] == FA_KV_STAGES) ps[g] = 0;
+          progress = true;
+        }
       }
-      if (m + 1 < m_total) advance_s();
-      if (++pj == nt) pj = 0;
-      if (++ps == FA_KV_STAGES) ps = 0;
+      if (progress) idle = 0;
+      else if (++idle > (1u << 26)) __trap();   // protocol bug -> trap instead of a hang
     }
   } else {
     const int g = (warp - 2) >> 2;        // query tile of the pair
@@ -230,88 +241,89 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
         mbar_wait(s_full(g), m & 1);
         tc_fence_after();
         if (!dead) {
-          const int nvalid = T - j * FA_BN;                    // existing keys of this tile
-          const int kc = j == nt - 1 ? kc_last : FA_BN;        // key columns the MMAs cover
-          uint32_t v[64];
-          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-          uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-          // ---- pass 1: row maximum. Keys 64..127 first, then keys 0..63, which stay in registers for pass 2
-          float mx = m_run;
-          if (kc > 64) {
-            tmem_ld_32x32(s_col + 64, v0);
-            tmem_ld_32x32(s_col + 96, v1);
-            tmem_ld_wait();
-            if (nvalid < FA_BN) {   // keys beyond T (only in the last tile): score -inf -> probability exactly 0
+          // one key tile; FULL = all 128 key columns exist (straight-line code, no masks), otherwise the last tile
+          auto tile = [&](auto full_c) {
+            constexpr bool FULL = decltype(full_c)::value;
+            const int nvalid = FULL ? FA_BN : T - j * FA_BN;      // existing keys of this tile
+            const int kc = FULL ? FA_BN : kc_last;                // key columns the MMAs cover
+            uint32_t v[64];
+            uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+            uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+            auto load_half = [&](int hf) {   // scores of keys [64 hf, 64 hf + 64); keys beyond T -> -inf -> P exactly 0
+              tmem_ld_32x32(s_col + hf * 64, v0);
+              tmem_ld_32x32(s_col + hf * 64 + 32, v1);
+              tmem_ld_wait();
+              if (!FULL) {
 #pragma unroll
-              for (int i = 0; i < 64; ++i)
-                if (64 + i >= nvalid) v[i] = 0xff800000u;
+                for (int i = 0; i < 64; ++i)
+                  if (hf * 64 + i >= nvalid) v[i] = 0xff800000u;
+              }
+            };
+            // ---- pass 1: row maximum. Keys 64..127 first, then keys 0..63, which stay in registers for pass 2
+            float mx = m_run;
+            if (FULL || kc > 64) {
+              load_half(1);
+#pragma unroll
+              for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
             }
+            load_half(0);
 #pragma unroll
             for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
-          tmem_ld_32x32(s_col, v0);
-          tmem_ld_32x32(s_col + 32, v1);
-          tmem_ld_wait();
-          if (nvalid < 64) {
+            if (!FULL && kc <= 64) {   // nothing more to read from S_g: let the next score tile start
+              tc_fence_before();
+              mbar_arrive(s_free(g));
+            }
+            if (m == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+            const float corr = ex2_approx((m_run - mx) * sc);   // first tile: exp2(-inf) = 0
+            const float msc = mx * sc;
+            m_run = mx;
+            // P_g is single buffered: P_g V_{j-1} must have finished reading it (issued long ago: no stall in practice)
+            if (j > 0) mbar_wait(o_full(g, (m - 1) & 1), ((m - 1) >> 1) & 1);
+            // ---- pass 2: P = 2^(s*c - m*c), row sum, fp16 P into the swizzled K-major atoms
+            float rs = 0.f;
+            auto exp_store = [&](uint32_t pr, int cols) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (i >= nvalid) v[i] = 0xff800000u;
-          }
+              for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 keys = 16 bytes each; chunk c of the row sits at slot c ^ (r % 8)
+                if (FULL || c * 8 < cols) {
+                  uint32_t pk[4];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          if (m == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
-          const float corr = ex2_approx((m_run - mx) * sc);   // first tile: exp2(-inf) = 0
-          const float msc = mx * sc;
-          m_run = mx;
-          // P_g is single buffered: P_g V_{j-1} must have finished reading it (it was issued before S_g(j) completed,
-          // so this wait does not stall in practice)
-          if (j > 0) mbar_wait(o_full(g, (m - 1) & 1), ((m - 1) >> 1) & 1);
-          // ---- pass 2: P = 2^(s*c - m*c), row sum, fp16 P into the swizzled K-major atoms
-          float rs = 0.f;
-          auto exp_store = [&](uint32_t pr, int cols) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 keys = 16 bytes each; chunk c of the row sits at slot c ^ (r % 8)
-              if (c * 8 < cols) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                  const int i = c * 8 + e;
-                  const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -msc));
-                  const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -msc));
-                  rs += p0 + p1;
-                  pk[e >> 1] = pack_half2(p0, p1);
+                  for (int e = 0; e < 8; e += 2) {
+                    const int i = c * 8 + e;
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -msc));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -msc));
+                    rs += p0 + p1;
+                    pk[e >> 1] = pack_half2(p0, p1);
+                  }
+                  const uint32_t addr = pr + (((c ^ (r & 7))) << 4);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]),
+                               "r"(pk[2]), "r"(pk[3])
+                               : "memory");
                 }
-                const uint32_t addr = pr + (((c ^ (r & 7))) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                             "r"(pk[3])
-                             : "memory");
               }
+            };
+            exp_store(prow, kc);   // keys 0..63 (or the first kc of them)
+            if (FULL || kc > 64) {
+              load_half(1);
+              tc_fence_before();
+              mbar_arrive(s_free(g));   // last read of S_g: S_g(j+1) is computed while the second half is exponentiated
+              exp_store(prow + FA_TILE, kc - 64);
             }
+            l_run = l_run * corr + rs;
+            fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+            tc_fence_before();          // order the TMEM reads of O_g(j-2) before the MMA that overwrites it
+            mbar_arrive(p_full(g));
+            // accumulate the PREVIOUS tile's P V product (complete, see the o_full wait above)
+            if (j > 0) {
+              tc_fence_after();
+              accumulate_o(m - 1, corr_prev);
+            }
+            corr_prev = corr;
           };
-          exp_store(prow, kc);   // keys 0..63 (or the first kc of them)
-          if (kc > 64) {
-            tmem_ld_32x32(s_col + 64, v0);
-            tmem_ld_32x32(s_col + 96, v1);
-            tmem_ld_wait();
-            if (nvalid < FA_BN) {
-#pragma unroll
-              for (int i = 0; i < 64; ++i)
-                if (64 + i >= nvalid) v[i] = 0xff800000u;
-            }
-            exp_store(prow + FA_TILE, kc - 64);
-          }
-          l_run = l_run * corr + rs;
-          fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
-          tc_fence_before();          // order the TMEM reads of S_g (and of O_g(j-2)) before the MMAs that overwrite them
-          mbar_arrive(p_full(g));
-          // accumulate the PREVIOUS tile's P V product (complete, see the o_full wait above)
-          if (j > 0) {
-            tc_fence_after();
-            accumulate_o(m - 1, corr_prev);
-          }
-          corr_prev = corr;
+          if (j < nt - 1 || (T & (FA_BN - 1)) == 0) tile(std::true_type{});
+          else tile(std::false_type{});
         } else {
           tc_fence_before();
+          mbar_arrive(s_free(g));
           mbar_arrive(p_full(g));
         }
       }
