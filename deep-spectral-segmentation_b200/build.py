@@ -16,7 +16,7 @@ CSRC = HERE / "csrc"
 LIB = HERE / "libdss_b200.so"
 SOURCES = ["api.cu", "gemm.cu", "vit_kernels.cu", "attention_tc.cu", "vit.cu", "affinity.cu", "eigsh.cu", "knn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--use_fast_math=false" if False else "-DDSS_BUILD", "-Xptxas", "-v"]
+              "-DDSS_BUILD", "-Xptxas", "-v", *os.environ.get("DSS_EXTRA_NVCC_FLAGS", "").split()]
 
 
 def _nvcc() -> str:

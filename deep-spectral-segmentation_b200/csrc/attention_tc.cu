@@ -6,22 +6,25 @@
 //   warp 0      TMA producer: Q tiles (double buffered per query tile) and K_j / V_j tiles straight out of the packed
 //               qkv activations [B*T, 3d] (box 64 x 128, 128 B swizzle) through a 3-stage ring shared by both
 //               query tiles
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, per query tile g in {A, B} and key tile j:
-//                 S_g = Q_g K_j^T  (UMMA 128 x kc x 16, x4, both operands K-major)               -> TMEM S_g
-//                 O_g = P_g V_j    (UMMA 128 x 64 x 16, x kc/16, A = P from smem, B = V MN-major) -> TMEM O_g[j & 1]
+//   warps 1, 2  tcgen05.mma issuers of query tile A / B (warp 1 also owns the TMEM allocation); per key tile j:
+//                 S_g = Q_g K_j^T   (UMMA 128 x kc x 16, x4, both operands K-major)               -> TMEM S_g
+//                 O_g += P_g V_j    (UMMA 128 x 64 x 16, x kc/16, A = P from smem, B = V MN-major) -> TMEM O_g
 //               kc = 128 except in the last key tile, where it is the number of existing keys rounded up to 16
-//               (T = 901: 16 instead of 128). S_g(j+1) is issued as soon as the softmax warps have read S_g(j), BEFORE
-//               P_g V_j.
-//   warps 2..5  softmax of query tile A, warps 6..9 of query tile B: ONE thread per query row (tcgen05.ld 32x32b), no
-//               cross-thread exchange. Pass 1 reads the 128 scores for the row maximum (the second half read stays in
-//               registers), pass 2 computes P = 2^(s c - m c) (MUFU.EX2), the row sum, and writes P as fp16 into the
-//               K-major 128 B-swizzled smem tiles the PV MMA reads. The output is accumulated in REGISTERS one tile
-//               late (o = o * 2^(m_{j-1} - m_j) + O_j after P_{j+1} has been published), so a softmax warp never waits
-//               for a tensor-core result issued in the same iteration.
-// The two softmax groups run out of phase (B's first tile is held back until A has finished its first pass 1), so one
-// group's MUFU-bound exp phase overlaps the other's TMEM loads / maxima / fences / O accumulation. The kernel is bound
-// by the MUFU pipe (128 x 128 exp2 per tile at 16 per clock per SM), not by the tensor pipe.
+//               (T = 901: 16 instead of 128).
+//   warps 4..7  softmax of query tile A, warps 8..11 of query tile B: ONE thread per query row (tcgen05.ld 32x32b), no
+//               cross-thread exchange. The 128 scores of the row are read from TMEM once and S_g is released at once
+//               (the next score tile is computed while this one is exponentiated); P = 2^(s c - m c) (MUFU.EX2) goes
+//               as fp16 into the K-major 128 B-swizzled smem tiles the PV MMA reads.
+//               The output accumulates in TMEM across key tiles. The reference maximum m is only raised (and O, l
+//               rescaled, by the owning thread through tcgen05.ld/st) when a tile's row maximum exceeds it by more than
+//               2^8 -- softmax is shift invariant and fp16 P / fp32 sums have the headroom -- so in the steady state the
+//               softmax warps never touch O until the epilogue.
+// The two softmax groups run out of phase (B's first tile is held back until A has read its first score tile), so one
+// group's MUFU-bound exp phase overlaps the other's TMEM loads / maxima / fences. The kernel is bound by the MUFU pipe
+// (128 x 128 exp2 per tile at 16 per clock per SM), not by the tensor pipe.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -38,16 +41,28 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64, FA_THREADS = 320;   // TMA warp + MMA warp + 2 x 4 softmax warps
+// warp group 0: TMA warp, two MMA warps, one idle warp; warp groups 1 / 2: softmax of query tile A / B.
+// Register budget (setmaxnreg, per warp group): 168 at launch -> 56 for group 0, 224 for the softmax groups
+// (4 x 32 x (56 + 224 + 224) = 64512 <= 65536).
+constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64, FA_THREADS = 384;
 constexpr int FA_TILE = FA_BM * FA_D * 2;             // 16 KB: one [128 x 64] fp16 tile
 constexpr int FA_KV_STAGES = 3;
 // Q[g][2] | K ring | V ring | P[g] (two 64-key atoms each) = 14 tiles = 224 KB
 constexpr int FA_SMEM = FA_TILE * (4 + 2 * FA_KV_STAGES + 4);
 constexpr int FA_TMEM_COLS = 512;
-constexpr int FA_S_COL = 0, FA_O_COL = 256;   // S_A, S_B at columns 0 / 128; O_g[i] at 256 + 128 g + 64 i
+constexpr int FA_S_COL = 0, FA_O_COL = 256;   // S_A, S_B at columns 0 / 128; O_A, O_B at 256 / 320
+constexpr float FA_RESCALE_LOG2 = 8.0f;       // raise the reference maximum only when exceeded by more than 2^8
+#ifdef DSS_ATTN_ABLATION
+__device__ long long* g_attn_trace = nullptr;   // tuning only: per-phase clock64 stamps of CTA 0
+#define FA_TRACE(slot) do { if (trace) trace[(slot)] = clock64(); } while (0)
+#else
+#define FA_TRACE(slot) do { } while (0)
+#endif
 constexpr int FA_NBARS = 8 + 2 * FA_KV_STAGES + 10;
 
-// 10 warps = 3 on some SM sub-partitions: 16 K registers / (3 x 32 threads) caps the kernel at 168 registers
+// ABL: timing-ablation bits (tuning only; any non-zero value computes garbage): 1 no exp2, 2 no P stores / fence,
+// 4 no row maximum, 8 no P V MMAs, 16 no score MMAs, 32 no row sum
+template <int ABL>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int heads,
                          int nq2, int total_items) {
@@ -65,10 +80,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
   auto kv_empty = [&](int s) { return bar0 + 8u * (8 + FA_KV_STAGES + s); };
   auto s_full = [&](int g) { return bar0 + 8u * (8 + 2 * FA_KV_STAGES + g); };
   auto p_full = [&](int g) { return bar0 + 8u * (10 + 2 * FA_KV_STAGES + g); };
-  auto o_full = [&](int g, int i) { return bar0 + 8u * (12 + 2 * FA_KV_STAGES + g * 2 + i); };
+  auto o_full = [&](int g) { return bar0 + 8u * (12 + 2 * FA_KV_STAGES + g); };
   auto s_free = [&](int g) { return bar0 + 8u * (16 + 2 * FA_KV_STAGES + g); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef DSS_ATTN_ABLATION
+  long long* trace = (blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2 || warp >= 4)) ? g_attn_trace : nullptr;
+#endif
   const int d = heads * FA_D;
   const int nt = (T + FA_BN - 1) / FA_BN;
   const int kc_last = (T - (nt - 1) * FA_BN + 15) & ~15;   // key columns of the last tile that are worth computing
@@ -78,16 +96,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
     for (int i = 0; i < 4; ++i) {
       mbar_init(q_full(i >> 1, i & 1), 1);
       mbar_init(q_empty(i >> 1, i & 1), 1);
-      mbar_init(o_full(i >> 1, i & 1), 1);
     }
     for (int s = 0; s < FA_KV_STAGES; ++s) {
       mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(kv_empty(s), 2);   // one commit per query tile's MMA warp
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full(g), 1);
-      mbar_init(p_full(g), 128);
-      mbar_init(s_free(g), 128);
+      mbar_init(p_full(g), 4);   // one arrival per softmax warp: 128 per-thread arrivals on one barrier serialise
+      mbar_init(s_free(g), 4);   // (measured: ~1300 cycles until the phase flips)
+      mbar_init(o_full(g), 1);
     }
     mbar_fence_init();
   }
@@ -103,6 +121,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
   // Producer and MMA warps run their loops with ALL lanes on warp-uniform values and let one elected lane issue: the
   // smem addresses, coordinates and descriptors then live in uniform registers and each UMMA / TMA issue is a couple
   // of instructions instead of a register-to-uniform "waterfall" loop.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     const uint32_t uQ = __shfl_sync(0xffffffffu, sQ, 0), uK = __shfl_sync(0xffffffffu, sK, 0),
                    uV = __shfl_sync(0xffffffffu, sV, 0);
@@ -134,85 +154,82 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
         if (++s == FA_KV_STAGES) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2) {
+    // one MMA-issuing warp per query tile (a single warp serving both tiles was the bottleneck of the kernel: ~1000
+    // cycles per batch of UMMAs, four batches per step). Per tile the events strictly alternate in time
+    // (S_g released early in key tile n, P_g published at its end), so plain blocking waits in program order suffice.
+    const int g = warp - 1;
     constexpr uint32_t idesc_qk0 = umma_idesc_f16(FA_BM, 0);                    // A, B K-major; N filled in per tile
     constexpr uint32_t idesc_pv = umma_idesc_f16(FA_BM, FA_D) | (1u << 16);     // B (= V) MN-major
-    const uint32_t uQ = __shfl_sync(0xffffffffu, sQ, 0), uK = __shfl_sync(0xffffffffu, sK, 0),
-                   uV = __shfl_sync(0xffffffffu, sV, 0), uP = __shfl_sync(0xffffffffu, sP, 0),
+    const uint32_t uQ = __shfl_sync(0xffffffffu, sQ, 0) + g * 2 * FA_TILE, uK = __shfl_sync(0xffffffffu, sK, 0),
+                   uV = __shfl_sync(0xffffffffu, sV, 0), uP = __shfl_sync(0xffffffffu, sP, 0) + g * 2 * FA_TILE,
                    utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t s_acc = utmem + FA_S_COL + g * FA_BN, o_acc = utmem + FA_O_COL + g * FA_D;
+    const uint64_t p0 = umma_desc_sw128(uP);              // keys 0..63 (K-major atom)
+    const uint64_t p1 = umma_desc_sw128(uP + FA_TILE);    // keys 64..127
     const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
     const int m_total = my_items * nt;   // key-tile steps of this CTA, over all of its items
-    // Event loop: each query tile g has a cursor for its next score tile (needs S_g released by the softmax warps)
-    // and one for its next P V product (needs P_g published); whichever is ready is issued.
-    int ns[2] = {0, 0}, sj[2] = {0, 0}, sq[2] = {0, 0}, ss[2] = {0, 0};     // score cursor: step, key tile, item, ring stage
-    uint32_t sph[2] = {0, 0};
-    int np[2] = {0, 0}, pj[2] = {0, 0}, ps[2] = {0, 0};                      // P V cursor
-    uint32_t idle = 0;
-    while (np[0] < m_total || np[1] < m_total) {
-      bool progress = false;
+    int sj = 0, sq = 0, ss = 0;          // cursor of the next score tile: key tile, item, ring stage
+    uint32_t sph = 0;
+    auto issue_s = [&]() {   // S_g = Q_g K_j^T
+      if (sj == 0) mbar_wait(q_full(g, sq & 1), (sq >> 1) & 1);
+      mbar_wait(kv_full(ss), sph);
+      tc_fence_after();
+      const uint64_t qdesc = umma_desc_sw128(uQ + (sq & 1) * FA_TILE);
+      const uint64_t kdesc = umma_desc_sw128(uK + ss * FA_TILE);
+      const int kc = sj == nt - 1 ? kc_last : FA_BN;
+      const uint32_t idesc = idesc_qk0 | (static_cast<uint32_t>(kc >> 3) << 17);
+      if (elect_one()) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        // ---- S_g(n) = Q_g K_j^T: S_g is free once the softmax warps have read S_g(n-1) for the last time
-        // (all probes are non-blocking: a blocking wait for K_j here could starve the other query tile's P V product,
-        // which is what releases the ring slot K_j is waiting for)
-        if (ns[g] < m_total && (ns[g] == 0 || mbar_test_all(s_free(g), (ns[g] - 1) & 1)) &&
-            mbar_test_all(kv_full(ss[g]), sph[g]) &&
-            (sj[g] != 0 || mbar_test_all(q_full(g, sq[g] & 1), (sq[g] >> 1) & 1))) {
-          tc_fence_after();
-          const uint64_t qdesc = umma_desc_sw128(uQ + (g * 2 + (sq[g] & 1)) * FA_TILE);
-          const uint64_t kdesc = umma_desc_sw128(uK + ss[g] * FA_TILE);
-          const int kc = sj[g] == nt - 1 ? kc_last : FA_BN;
-          const uint32_t idesc = idesc_qk0 | (static_cast<uint32_t>(kc >> 3) << 17);
-          const uint32_t acc = utmem + FA_S_COL + g * FA_BN;
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < FA_D / 16; ++k)   // +32 B per 16-wide K step = +2 in the descriptor's address field
-              umma_f16_ss(acc, qdesc + 2u * k, kdesc + 2u * k, idesc, k != 0 ? 1u : 0u);
-            umma_commit(s_full(g));
-            if (sj[g] == nt - 1) umma_commit(q_empty(g, sq[g] & 1));   // last score tile of the item: Q_g may be replaced
-          }
-          __syncwarp();
-          ++ns[g];
-          if (++sj[g] == nt) { sj[g] = 0; ++sq[g]; }
-          if (++ss[g] == FA_KV_STAGES) { ss[g] = 0; sph[g] ^= 1u; }
-          progress = true;
-        }
-        // ---- O_g[n & 1] = P_g V_j once the softmax warps have published P_g(n) (they consumed O_g(n-2) before that)
-        if (np[g] < m_total && mbar_test_all(p_full(g), np[g] & 1)) {
-          tc_fence_after();
-          const int n = np[g];
-          const int ksteps = (pj[g] == nt - 1 ? kc_last : FA_BN) >> 4;
-          const uint64_t vdesc = umma_desc_sw128(uV + ps[g] * FA_TILE);   // +16 key rows = +2048 B = +128
-          const uint64_t p0 = umma_desc_sw128(uP + g * 2 * FA_TILE);              // keys 0..63 (K-major atom)
-          const uint64_t p1 = umma_desc_sw128(uP + g * 2 * FA_TILE + FA_TILE);    // keys 64..127
-          const uint32_t acc = utmem + FA_O_COL + g * 2 * FA_D + (n & 1) * FA_D;
-          const bool release = np[g ^ 1] > n;   // the other query tile has already issued its P V_j: K_j / V_j are done
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < FA_BN / 16; ++k)
-              if (k < ksteps)
-                umma_f16_ss(acc, (k < 4 ? p0 : p1) + 2u * (k & 3), vdesc + 128u * k, idesc_pv, k != 0 ? 1u : 0u);
-            umma_commit(o_full(g, n & 1));
-            if (release) umma_commit(kv_empty(ps[g]));
-          }
-          __syncwarp();
-          ++np[g];
-          if (++pj[g] == nt) pj[g] = 0;
-          if (++ps[g] == FA_KV_STAGES) ps[g] = 0;
-          progress = true;
-        }
+        for (int k = 0; k < FA_D / 16; ++k)   // +32 B per 16-wide K step = +2 in the descriptor's address field
+          if (!(ABL & 16)) umma_f16_ss(s_acc, qdesc + 2u * k, kdesc + 2u * k, idesc, k != 0 ? 1u : 0u);
+        umma_commit(s_full(g));
+        if (sj == nt - 1) umma_commit(q_empty(g, sq & 1));   // last score tile of the item: Q_g may be replaced
       }
-      if (progress) idle = 0;
-      else if (++idle > (1u << 26)) __trap();   // protocol bug -> trap instead of a hang
+      __syncwarp();
+      if (++sj == nt) { sj = 0; ++sq; }
+      if (++ss == FA_KV_STAGES) { ss = 0; sph ^= 1u; }
+    };
+    if (m_total > 0) issue_s();
+    int pj = 0, ps = 0;
+    for (int n = 0; n < m_total; ++n) {
+      if (n + 1 < m_total) {   // S_g(n+1) as soon as the softmax warps hold S_g(n) in registers
+        mbar_wait(s_free(g), n & 1);
+        FA_TRACE(8192 + g * 2048 + (n < 500 ? n : 500) * 4 + 0);
+        issue_s();
+        FA_TRACE(8192 + g * 2048 + (n < 500 ? n : 500) * 4 + 1);
+      }
+      // O_g (+)= P_g V_j once the softmax warps have published P_g(n) (and rescaled O_g if they had to)
+      mbar_wait(p_full(g), n & 1);
+      tc_fence_after();
+      FA_TRACE(8192 + g * 2048 + (n < 500 ? n : 500) * 4 + 2);
+      const int ksteps = (pj == nt - 1 ? kc_last : FA_BN) >> 4;
+      const uint64_t vdesc = umma_desc_sw128(uV + ps * FA_TILE);   // +16 key rows = +2048 B = +128
+      const bool first = pj == 0;   // first key tile of the item: overwrite
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k)
+          if (k < ksteps && !(ABL & 8))
+            umma_f16_ss(o_acc, (k < 4 ? p0 : p1) + 2u * (k & 3), vdesc + 128u * k, idesc_pv,
+                        (k != 0 || !first) ? 1u : 0u);
+        umma_commit(o_full(g));
+        umma_commit(kv_empty(ps));   // this query tile is done with K_j / V_j (the ring slot needs both tiles' commits)
+      }
+      __syncwarp();
+      FA_TRACE(8192 + g * 2048 + (n < 500 ? n : 500) * 4 + 3);
+      if (++pj == nt) pj = 0;
+      if (++ps == FA_KV_STAGES) ps = 0;
     }
+  }
   } else {
-    const int g = (warp - 2) >> 2;        // query tile of the pair
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = (warp - 4) >> 2;        // query tile of the pair
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;          // query row inside the tile
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t s_col = lane_addr + FA_S_COL + g * FA_BN;
-    const uint32_t o_col = lane_addr + FA_O_COL + g * 2 * FA_D;
+    const uint32_t o_col = lane_addr + FA_O_COL + g * FA_D;
     const uint32_t prow = sP + g * 2 * FA_TILE + r * 128;   // this row inside the first P atom; second atom + FA_TILE
     const float sc = 1.4426950408889634f * 0.125f;  // log2(e) / sqrt(64)
     uint32_t m = 0;   // key-tile step counter of this CTA (all barrier phases derive from it)
@@ -220,130 +237,138 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
       const int qp = w % nq2, bh = w / nq2;
       const int h = bh % heads, row0 = (bh / heads) * T;
       const int q0 = (2 * qp + g) * FA_BM;
-      const bool dead = q0 >= T;   // odd number of query tiles: nothing to do for B in the last pair
-      float m_run = -INFINITY, l_run = 0.f;
-      float corr_prev = 0.f;       // rescale factor that goes with the not-yet-accumulated O_{j-1}
-      float o[FA_D];
-#pragma unroll
-      for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
-      auto accumulate_o = [&](uint32_t mm, float corr) {   // o = o * corr + O(mm)
-        uint32_t t[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld_32x32(o_col + (mm & 1) * FA_D + c * 32, t);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], corr, __uint_as_float(t[i]));
-        }
-      };
+      const bool dead = q0 >= T || ((ABL & 64) && g == 1);   // odd number of query tiles: nothing to do for B in the last pair
+      float m_ref = -INFINITY, l_run = 0.f;   // reference maximum of the exponent, row sum relative to it
       for (int j = 0; j < nt; ++j, ++m) {
         if (m == 0 && g == 1) asm volatile("bar.sync 3, 256;" ::: "memory");   // start half a period behind tile A
         mbar_wait(s_full(g), m & 1);
         tc_fence_after();
+        const int tb = (warp - 4) * 1024 + (m < 120 ? m : 120) * 8;
+        FA_TRACE(tb + 0);
         if (!dead) {
-          // one key tile; FULL = all 128 key columns exist (straight-line code, no masks), otherwise the last tile
-          auto tile = [&](auto full_c) {
-            constexpr bool FULL = decltype(full_c)::value;
-            const int nvalid = FULL ? FA_BN : T - j * FA_BN;      // existing keys of this tile
-            const int kc = FULL ? FA_BN : kc_last;                // key columns the MMAs cover
-            uint32_t v[64];
-            uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-            uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-            auto load_half = [&](int hf) {   // scores of keys [64 hf, 64 hf + 64); keys beyond T -> -inf -> P exactly 0
-              tmem_ld_32x32(s_col + hf * 64, v0);
-              tmem_ld_32x32(s_col + hf * 64 + 32, v1);
-              tmem_ld_wait();
-              if (!FULL) {
+          // one key tile, in four chunks of 32 key columns; only the last tile of a row of tiles can be short
+          // (kc < 128 columns computed, nvalid <= kc of them real keys)
+          const bool tail = j == nt - 1 && (T & (FA_BN - 1)) != 0;
+          const int kc = tail ? kc_last : FA_BN;
+          const int nvalid = tail ? T - j * FA_BN : FA_BN;
+          uint32_t v[128];
 #pragma unroll
-                for (int i = 0; i < 64; ++i)
-                  if (hf * 64 + i >= nvalid) v[i] = 0xff800000u;
+          for (int c = 0; c < 4; ++c)
+            if (c * 32 < kc) tmem_ld_32x32(s_col + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&v[c * 32]));
+          tmem_ld_wait();
+          FA_TRACE(tb + 1);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free(g));   // S_g is in registers: the next score tile may overwrite it
+          if (m == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c * 32 < kc) {
+              if (tail) {   // keys beyond T: score -inf -> probability exactly 0
+#pragma unroll
+                for (int i = c * 32; i < c * 32 + 32; ++i)
+                  if (i >= nvalid) v[i] = 0xff800000u;
               }
-            };
-            // ---- pass 1: row maximum. Keys 64..127 first, then keys 0..63, which stay in registers for pass 2
-            float mx = m_run;
-            if (FULL || kc > 64) {
-              load_half(1);
 #pragma unroll
-              for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+              for (int i = c * 32; i < c * 32 + 32; ++i)
+                if (!(ABL & 4)) mx = fmaxf(mx, __uint_as_float(v[i]));
             }
-            load_half(0);
+          }
+          FA_TRACE(tb + 2);
+          // P_g is single buffered and O_g accumulates in place: P_g V_{j-1} must be complete (issued long ago)
+          if (j > 0) {
+            mbar_wait(o_full(g), (m - 1) & 1);
+            tc_fence_after();
+          }
+          if (j == 0) {
+            m_ref = mx;
+          } else {
+            const bool raise = (mx - m_ref) * sc > FA_RESCALE_LOG2;
+            if (__any_sync(0xffffffffu, raise)) {   // rare: rescale this warp's rows of O_g in TMEM
+              const float f = raise ? ex2_approx((m_ref - mx) * sc) : 1.0f;
+              uint32_t t[32];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-            if (!FULL && kc <= 64) {   // nothing more to read from S_g: let the next score tile start
-              tc_fence_before();
-              mbar_arrive(s_free(g));
+              for (int c = 0; c < 2; ++c) {
+                tmem_ld_32x32(o_col + c * 32, t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
+                tmem_st_32x32(o_col + c * 32, t);
+              }
+              tmem_st_wait();
+              l_run *= f;
+              if (raise) m_ref = mx;
             }
-            if (m == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
-            const float corr = ex2_approx((m_run - mx) * sc);   // first tile: exp2(-inf) = 0
-            const float msc = mx * sc;
-            m_run = mx;
-            // P_g is single buffered: P_g V_{j-1} must have finished reading it (issued long ago: no stall in practice)
-            if (j > 0) mbar_wait(o_full(g, (m - 1) & 1), ((m - 1) >> 1) & 1);
-            // ---- pass 2: P = 2^(s*c - m*c), row sum, fp16 P into the swizzled K-major atoms
-            float rs = 0.f;
-            auto exp_store = [&](uint32_t pr, int cols) {
+          }
+          FA_TRACE(tb + 3);
+          const float msc = m_ref * sc;
+          // ---- P = 2^(s*c - m*c), row sum, fp16 P into the swizzled K-major atoms
+          float rs = 0.f;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 keys = 16 bytes each; chunk c of the row sits at slot c ^ (r % 8)
-                if (FULL || c * 8 < cols) {
-                  uint32_t pk[4];
+          for (int c = 0; c < 4; ++c) {
+            if (c * 32 < kc) {
 #pragma unroll
-                  for (int e = 0; e < 8; e += 2) {
-                    const int i = c * 8 + e;
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -msc));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -msc));
-                    rs += p0 + p1;
-                    pk[e >> 1] = pack_half2(p0, p1);
-                  }
-                  const uint32_t addr = pr + (((c ^ (r & 7))) << 4);
+              for (int u = 0; u < 4; ++u) {   // 8 keys = 16 bytes; chunk x of the row sits at slot (x % 8) ^ (r % 8) of atom x / 8
+                const int x = c * 4 + u;
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  const int i = x * 8 + e;
+                  const float x0 = fmaf(__uint_as_float(v[i]), sc, -msc), x1 = fmaf(__uint_as_float(v[i + 1]), sc, -msc);
+                  const float p0 = (ABL & 1) ? x0 : ex2_approx(x0);
+                  const float p1 = (ABL & 1) ? x1 : ex2_approx(x1);
+                  if (!(ABL & 32)) rs += p0 + p1;
+                  pk[e >> 1] = pack_half2(p0, p1);
+                }
+                const uint32_t addr = prow + (x >> 3) * FA_TILE + ((((x & 7) ^ (r & 7))) << 4);
+                if (!(ABL & 2))
                   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]),
                                "r"(pk[2]), "r"(pk[3])
                                : "memory");
-                }
+                else
+                  rs += __uint_as_float(pk[0] ^ pk[1] ^ pk[2] ^ pk[3]);   // keep the values alive
               }
-            };
-            exp_store(prow, kc);   // keys 0..63 (or the first kc of them)
-            if (FULL || kc > 64) {
-              load_half(1);
-              tc_fence_before();
-              mbar_arrive(s_free(g));   // last read of S_g: S_g(j+1) is computed while the second half is exponentiated
-              exp_store(prow + FA_TILE, kc - 64);
             }
-            l_run = l_run * corr + rs;
-            fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
-            tc_fence_before();          // order the TMEM reads of O_g(j-2) before the MMA that overwrites it
-            mbar_arrive(p_full(g));
-            // accumulate the PREVIOUS tile's P V product (complete, see the o_full wait above)
-            if (j > 0) {
-              tc_fence_after();
-              accumulate_o(m - 1, corr_prev);
-            }
-            corr_prev = corr;
-          };
-          if (j < nt - 1 || (T & (FA_BN - 1)) == 0) tile(std::true_type{});
-          else tile(std::false_type{});
+          }
+          FA_TRACE(tb + 4);
+          l_run += rs;
+          if (!(ABL & 2)) fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+          tc_fence_before();          // order this thread's TMEM accesses before the MMA that accumulates into O_g
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full(g));
+          FA_TRACE(tb + 5);
         } else {
+          // nothing to compute, but keep the protocol: P_g(m) may only be announced once P_g V(m-1) has been issued
+          // (the MMA warp probes p_full by parity and must never be lapped by two phases)
+          if (m > 0) mbar_wait(o_full(g), (m - 1) & 1);
           tc_fence_before();
-          mbar_arrive(s_free(g));
-          mbar_arrive(p_full(g));
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(s_free(g));
+            mbar_arrive(p_full(g));
+          }
         }
       }
       if (!dead) {
-        const uint32_t ml = m - 1;   // last tile of this item
-        mbar_wait(o_full(g, ml & 1), (ml >> 1) & 1);
+        mbar_wait(o_full(g), (m - 1) & 1);   // last P V product of this item
         tc_fence_after();
-        accumulate_o(ml, corr_prev);
+        uint32_t t[FA_D];
+        tmem_ld_32x32(o_col, *reinterpret_cast<uint32_t (*)[32]>(&t[0]));
+        tmem_ld_32x32(o_col + 32, *reinterpret_cast<uint32_t (*)[32]>(&t[32]));
+        tmem_ld_wait();
         tc_fence_before();
         const float inv = 1.0f / l_run;
-        const int t = q0 + r;
-        if (t < T) {   // each thread owns one full 128-byte output row
-          uint4* og = reinterpret_cast<uint4*>(out + (long long)(row0 + t) * d + h * FA_D);
+        const int tq = q0 + r;
+        if (tq < T) {   // each thread owns one full 128-byte output row
+          uint4* og = reinterpret_cast<uint4*>(out + (long long)(row0 + tq) * d + h * FA_D);
 #pragma unroll
           for (int i = 0; i < FA_D; i += 8) {
             uint4 wv;
-            wv.x = pack_half2(o[i + 0] * inv, o[i + 1] * inv);
-            wv.y = pack_half2(o[i + 2] * inv, o[i + 3] * inv);
-            wv.z = pack_half2(o[i + 4] * inv, o[i + 5] * inv);
-            wv.w = pack_half2(o[i + 6] * inv, o[i + 7] * inv);
+            wv.x = pack_half2(__uint_as_float(t[i + 0]) * inv, __uint_as_float(t[i + 1]) * inv);
+            wv.y = pack_half2(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
+            wv.z = pack_half2(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv);
+            wv.w = pack_half2(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv);
             og[i >> 3] = wv;
           }
         }
@@ -357,10 +382,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
 
 int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cudaStream_t st) {
   DSS_REQUIRE(B > 0 && T > 0 && heads > 0, "attention: empty problem");
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSS_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    attr_set = true;
+  static int abl = -1;
+  if (abl < 0) {
+    const char* e = getenv("DSS_ATTN_ABL");   // tuning only
+    abl = e ? atoi(e) : 0;
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+#ifdef DSS_ATTN_ABLATION
+#define DSS_ABL_ATTR(n) DSS_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    DSS_ABL_ATTR(1) DSS_ABL_ATTR(2) DSS_ABL_ATTR(4) DSS_ABL_ATTR(8) DSS_ABL_ATTR(16) DSS_ABL_ATTR(32) DSS_ABL_ATTR(3) DSS_ABL_ATTR(7) DSS_ABL_ATTR(39) DSS_ABL_ATTR(24) DSS_ABL_ATTR(63) DSS_ABL_ATTR(64) DSS_ABL_ATTR(65) DSS_ABL_ATTR(127) DSS_ABL_ATTR(88)
+#endif
   }
   CUtensorMap tm;
   int rc = make_tmap_f16(&tm, qkv, B * T, 3 * heads * FA_D, FA_BM);
@@ -375,7 +405,29 @@ int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cud
   const int total = B * heads * nq2;
   const int grid = total < sm_count ? total : sm_count;   // persistent: one CTA per SM
   LaunchScope scope(st, KC_ATTENTION);
-  attention_tcgen05_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tm, reinterpret_cast<__half*>(out), T, heads, nq2, total);
+#ifdef DSS_ATTN_ABLATION
+  static long long* trace_dev = nullptr;
+  const char* trace_path = getenv("DSS_ATTN_TRACE");
+  if (trace_path && !trace_dev) {
+    DSS_CHECK_CUDA(cudaMalloc(&trace_dev, 16384 * sizeof(long long)));
+    DSS_CHECK_CUDA(cudaMemset(trace_dev, 0, 16384 * sizeof(long long)));
+    DSS_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace, &trace_dev, sizeof(trace_dev)));
+  }
+#define DSS_ABL_CASE(n) case n: attention_tcgen05_kernel<n><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, reinterpret_cast<__half*>(out), T, heads, nq2, total); break;
+  switch (abl) {
+    DSS_ABL_CASE(1) DSS_ABL_CASE(2) DSS_ABL_CASE(4) DSS_ABL_CASE(8) DSS_ABL_CASE(16) DSS_ABL_CASE(32) DSS_ABL_CASE(3) DSS_ABL_CASE(7) DSS_ABL_CASE(39) DSS_ABL_CASE(24) DSS_ABL_CASE(63) DSS_ABL_CASE(64) DSS_ABL_CASE(65) DSS_ABL_CASE(127) DSS_ABL_CASE(88)
+    default: attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, reinterpret_cast<__half*>(out), T, heads, nq2, total);
+  }
+  if (trace_path) {
+    static long long host[16384];
+    DSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    DSS_CHECK_CUDA(cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "wb");
+    if (f) { fwrite(host, sizeof(host), 1, f); fclose(f); }
+  }
+#else
+  attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, reinterpret_cast<__half*>(out), T, heads, nq2, total);
+#endif
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
 }
