@@ -8,18 +8,19 @@
 //               query tiles
 //   warps 1, 2  tcgen05.mma issuers of query tile A / B (warp 1 also owns the TMEM allocation); per key tile j:
 //                 S_g = Q_g K_j^T   (UMMA 128 x kc x 16, x4, both operands K-major)               -> TMEM S_g
-//                 O_g += P_g V_j    (UMMA 128 x 64 x 16, x kc/16, A = P from smem, B = V MN-major) -> TMEM O_g
+//                 O_g += P_g V_j    (UMMA 128 x 64 x 16, x kc/16, A = P from TMEM, B = V MN-major) -> TMEM O_g
 //               kc = 128 except in the last key tile, where it is the number of existing keys rounded up to 16
 //               (T = 901: 16 instead of 128).
 //   warps 4..7  softmax of query tile A, warps 8..11 of query tile B: ONE thread per query row (tcgen05.ld 32x32b), no
 //               cross-thread exchange. The 128 scores of the row are read from TMEM once and S_g is released at once
 //               (the next score tile is computed while this one is exponentiated); P = 2^(s c - m c) (MUFU.EX2) goes
-//               as fp16 into the K-major 128 B-swizzled smem tiles the PV MMA reads.
+//               back to TMEM as packed fp16 pairs (tcgen05.st) and is the A operand of the PV MMA: P never touches
+//               shared memory, whose bandwidth the K / V / Q operand reads need.
 //               The output accumulates in TMEM across key tiles. The reference maximum m is only raised (and O, l
 //               rescaled, by the owning thread through tcgen05.ld/st) when a tile's row maximum exceeds it by more than
 //               2^8 -- softmax is shift invariant and fp16 P / fp32 sums have the headroom -- so in the steady state the
 //               softmax warps never touch O until the epilogue.
-// The two softmax groups run out of phase (B's first tile is held back until A has read its first score tile), so one
+// The two softmax groups run out of phase (B's first tile is held back until A is half way through its first tile), so one
 // group's MUFU-bound exp phase overlaps the other's TMEM loads / maxima / fences. The kernel is bound by the MUFU pipe
 // (128 x 128 exp2 per tile at 16 per clock per SM), not by the tensor pipe.
 #include <math.h>
@@ -33,6 +34,7 @@
 namespace dss {
 
 int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
+int make_tmap_out3d_f16(CUtensorMap* tm, const void* ptr, int images, int rows, int cols);
 
 // one MUFU.EX2 (2 ulp), flushes denormal results to zero; exp2f would add range checks and fix-ups per element
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -44,13 +46,35 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // warp group 0: TMA warp, two MMA warps, one idle warp; warp groups 1 / 2: softmax of query tile A / B.
 // Register budget (setmaxnreg, per warp group): 168 at launch -> 56 for group 0, 224 for the softmax groups
 // (4 x 32 x (56 + 224 + 224) = 64512 <= 65536).
+// exp2 of two values on the FMA pipe (Cody-Waite split + degree-4 minimax polynomial on [-0.5, 0.5], max relative error
+// 2.7e-6 -- far below the fp16 rounding of P): a share of the exponentials is taken off the MUFU unit, which at 16 per
+// clock per SM is the busiest unit of this kernel. Inputs are <= ~8; anything below -125 (masked keys) clamps to 2^-125,
+// which packs to an fp16 zero.
+__device__ __forceinline__ void ex2_poly_x2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t x = pack_f32x2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t xf = add_f32x2(x, pack_f32x2(12582912.0f, 12582912.0f));          // integer part in the low mantissa bits
+  const uint64_t n = add_f32x2(xf, pack_f32x2(-12582912.0f, -12582912.0f));
+  const uint64_t f = fma_f32x2(n, pack_f32x2(-1.0f, -1.0f), x);                    // x - round(x) in [-0.5, 0.5]
+  uint64_t p = fma_f32x2(pack_f32x2(0.009570100344717503f, 0.009570100344717503f), f,
+                         pack_f32x2(0.05591786280274391f, 0.05591786280274391f));
+  p = fma_f32x2(p, f, pack_f32x2(0.240247443318367f, 0.240247443318367f));
+  p = fma_f32x2(p, f, pack_f32x2(0.6931217908859253f, 0.6931217908859253f));
+  p = fma_f32x2(p, f, pack_f32x2(0.9999992847442627f, 0.9999992847442627f));
+  float pa, pb, xa, xb;
+  unpack_f32x2(p, pa, pb);
+  unpack_f32x2(xf, xa, xb);
+  p0 = __int_as_float(__float_as_int(pa) + (__float_as_int(xa) << 23));             // p * 2^n through the exponent field
+  p1 = __int_as_float(__float_as_int(pb) + (__float_as_int(xb) << 23));
+}
+constexpr int FA_POLY_OF_4 = 1;   // of every 4 consecutive key pairs, this many go through ex2_poly_x2
+
 constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64, FA_THREADS = 384;
 constexpr int FA_TILE = FA_BM * FA_D * 2;             // 16 KB: one [128 x 64] fp16 tile
 constexpr int FA_KV_STAGES = 3;
-// Q[g][2] | K ring | V ring | P[g] (two 64-key atoms each) = 14 tiles = 224 KB
-constexpr int FA_SMEM = FA_TILE * (4 + 2 * FA_KV_STAGES + 4);
+// Q[g][2] | K ring | V ring | output staging[g] = 12 tiles = 192 KB (P never touches shared memory)
+constexpr int FA_SMEM = FA_TILE * (4 + 2 * FA_KV_STAGES + 2);
 constexpr int FA_TMEM_COLS = 512;
-constexpr int FA_S_COL = 0, FA_O_COL = 256;   // S_A, S_B at columns 0 / 128; O_A, O_B at 256 / 320
+constexpr int FA_S_COL = 0, FA_O_COL = 256, FA_P_COL = 384;   // S_A, S_B at 0 / 128; O_A, O_B at 256 / 320; P_A, P_B at 384 / 448
 constexpr float FA_RESCALE_LOG2 = 8.0f;       // raise the reference maximum only when exceeded by more than 2^8
 #ifdef DSS_ATTN_ABLATION
 __device__ long long* g_attn_trace = nullptr;   // tuning only: per-phase clock64 stamps of CTA 0
@@ -64,7 +88,7 @@ constexpr int FA_NBARS = 8 + 2 * FA_KV_STAGES + 10;
 // 4 no row maximum, 8 no P V MMAs, 16 no score MMAs, 32 no row sum
 template <int ABL>
 __global__ void __launch_bounds__(FA_THREADS, 1)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __restrict__ out, int T, int heads,
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, int T, int heads,
                          int nq2, int total_items) {
   extern __shared__ __align__(1024) uint8_t fa_smem[];
   __shared__ __align__(8) uint64_t bars[FA_NBARS];
@@ -72,7 +96,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
 
   const uint32_t base = smem_u32(fa_smem);
   if ((base & 1023u) != 0) __trap();  // the 128 B swizzle pattern is a function of address bits [7,10)
-  const uint32_t sQ = base, sK = base + 4 * FA_TILE, sV = sK + FA_KV_STAGES * FA_TILE, sP = sV + FA_KV_STAGES * FA_TILE;
+  const uint32_t sQ = base, sK = base + 4 * FA_TILE, sV = sK + FA_KV_STAGES * FA_TILE, sO = sV + FA_KV_STAGES * FA_TILE;
   const uint32_t bar0 = smem_u32(bars);
   auto q_full = [&](int g, int i) { return bar0 + 8u * (g * 2 + i); };
   auto q_empty = [&](int g, int i) { return bar0 + 8u * (4 + g * 2 + i); };
@@ -93,6 +117,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmO);
     for (int i = 0; i < 4; ++i) {
       mbar_init(q_full(i >> 1, i & 1), 1);
       mbar_init(q_empty(i >> 1, i & 1), 1);
@@ -162,11 +187,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
     constexpr uint32_t idesc_qk0 = umma_idesc_f16(FA_BM, 0);                    // A, B K-major; N filled in per tile
     constexpr uint32_t idesc_pv = umma_idesc_f16(FA_BM, FA_D) | (1u << 16);     // B (= V) MN-major
     const uint32_t uQ = __shfl_sync(0xffffffffu, sQ, 0) + g * 2 * FA_TILE, uK = __shfl_sync(0xffffffffu, sK, 0),
-                   uV = __shfl_sync(0xffffffffu, sV, 0), uP = __shfl_sync(0xffffffffu, sP, 0) + g * 2 * FA_TILE,
+                   uV = __shfl_sync(0xffffffffu, sV, 0),
                    utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t s_acc = utmem + FA_S_COL + g * FA_BN, o_acc = utmem + FA_O_COL + g * FA_D;
-    const uint64_t p0 = umma_desc_sw128(uP);              // keys 0..63 (K-major atom)
-    const uint64_t p1 = umma_desc_sw128(uP + FA_TILE);    // keys 64..127
+    const uint32_t p_tm = utmem + FA_P_COL + g * (FA_BN / 2);   // P_g: 128 rows x 128 fp16 = 64 columns
     const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
     const int m_total = my_items * nt;   // key-tile steps of this CTA, over all of its items
@@ -211,8 +235,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
 #pragma unroll
         for (int k = 0; k < FA_BN / 16; ++k)
           if (k < ksteps && !(ABL & 8))
-            umma_f16_ss(o_acc, (k < 4 ? p0 : p1) + 2u * (k & 3), vdesc + 128u * k, idesc_pv,
-                        (k != 0 || !first) ? 1u : 0u);
+            umma_f16_ts(o_acc, p_tm + 8u * k, vdesc + 128u * k, idesc_pv, (k != 0 || !first) ? 1u : 0u);
         umma_commit(o_full(g));
         umma_commit(kv_empty(ps));   // this query tile is done with K_j / V_j (the ring slot needs both tiles' commits)
       }
@@ -230,17 +253,19 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t s_col = lane_addr + FA_S_COL + g * FA_BN;
     const uint32_t o_col = lane_addr + FA_O_COL + g * FA_D;
-    const uint32_t prow = sP + g * 2 * FA_TILE + r * 128;   // this row inside the first P atom; second atom + FA_TILE
+    const uint32_t p_col = lane_addr + FA_P_COL + g * (FA_BN / 2);   // this row of P_g (fp16 pairs, 64 columns)
     const float sc = 1.4426950408889634f * 0.125f;  // log2(e) / sqrt(64)
     uint32_t m = 0;   // key-tile step counter of this CTA (all barrier phases derive from it)
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
       const int qp = w % nq2, bh = w / nq2;
-      const int h = bh % heads, row0 = (bh / heads) * T;
+      const int h = bh % heads;
       const int q0 = (2 * qp + g) * FA_BM;
       const bool dead = q0 >= T || ((ABL & 64) && g == 1);   // odd number of query tiles: nothing to do for B in the last pair
       float m_ref = -INFINITY, l_run = 0.f;   // reference maximum of the exponent, row sum relative to it
       for (int j = 0; j < nt; ++j, ++m) {
-        if (m == 0 && g == 1) asm volatile("bar.sync 3, 256;" ::: "memory");   // start half a period behind tile A
+        // tile B starts every item half a key tile behind tile A (A signals from the middle of its first tile): left
+        // alone, the two groups drift into lock step within ~10 items and both sit in their MUFU phase together
+        if (j == 0 && g == 1) asm volatile("bar.sync 3, 256;" ::: "memory");
         mbar_wait(s_full(g), m & 1);
         tc_fence_after();
         const int tb = (warp - 4) * 1024 + (m < 120 ? m : 120) * 8;
@@ -260,8 +285,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(s_free(g));   // S_g is in registers: the next score tile may overwrite it
-          if (m == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
-          float mx = -INFINITY;
+          float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c * 32 < kc) {
@@ -272,9 +296,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
               }
 #pragma unroll
               for (int i = c * 32; i < c * 32 + 32; ++i)
-                if (!(ABL & 4)) mx = fmaxf(mx, __uint_as_float(v[i]));
+                if (!(ABL & 4)) mxc[i & 3] = fmaxf(mxc[i & 3], __uint_as_float(v[i]));
             }
           }
+          const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
           FA_TRACE(tb + 2);
           // P_g is single buffered and O_g accumulates in place: P_g V_{j-1} must be complete (issued long ago)
           if (j > 0) {
@@ -303,37 +328,43 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
           }
           FA_TRACE(tb + 3);
           const float msc = m_ref * sc;
-          // ---- P = 2^(s*c - m*c), row sum, fp16 P into the swizzled K-major atoms
-          float rs = 0.f;
+          // ---- P = 2^(s*c - m*c), row sum, P as packed fp16 pairs into TMEM (the A operand of the P V product)
+          const uint64_t sc2 = pack_f32x2(sc, sc), nmsc2 = pack_f32x2(-msc, -msc);
+          uint64_t rs2[2] = {0ull, 0ull};   // packed partial row sums, two independent chains
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c * 32 < kc) {
+              uint32_t pk[16];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {   // 8 keys = 16 bytes; chunk x of the row sits at slot (x % 8) ^ (r % 8) of atom x / 8
-                const int x = c * 4 + u;
-                uint32_t pk[4];
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                  const int i = x * 8 + e;
-                  const float x0 = fmaf(__uint_as_float(v[i]), sc, -msc), x1 = fmaf(__uint_as_float(v[i + 1]), sc, -msc);
-                  const float p0 = (ABL & 1) ? x0 : ex2_approx(x0);
-                  const float p1 = (ABL & 1) ? x1 : ex2_approx(x1);
-                  if (!(ABL & 32)) rs += p0 + p1;
-                  pk[e >> 1] = pack_half2(p0, p1);
+              for (int e = 0; e < 32; e += 2) {
+                const int i = c * 32 + e;
+                float x0, x1;
+                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nmsc2), x0, x1);
+                constexpr int npoly = (ABL & 1024) ? 0 : ((ABL >> 8) & 3) ? ((ABL >> 8) & 3) : FA_POLY_OF_4;
+                float p0, p1;
+                if (((e >> 1) & 3) < npoly) {
+                  ex2_poly_x2(x0, x1, p0, p1);
+                } else {
+                  p0 = (ABL & 1) ? x0 : ex2_approx(x0);
+                  p1 = (ABL & 1) ? x1 : ex2_approx(x1);
                 }
-                const uint32_t addr = prow + (x >> 3) * FA_TILE + ((((x & 7) ^ (r & 7))) << 4);
-                if (!(ABL & 2))
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]),
-                               "r"(pk[2]), "r"(pk[3])
-                               : "memory");
-                else
-                  rs += __uint_as_float(pk[0] ^ pk[1] ^ pk[2] ^ pk[3]);   // keep the values alive
+                if (!(ABL & 32)) rs2[(e >> 1) & 1] = add_f32x2(rs2[(e >> 1) & 1], pack_f32x2(p0, p1));
+                pk[e >> 1] = pack_half2(p0, p1);
               }
+              if (!(ABL & 2)) tmem_st_32x16(p_col + c * 16, pk);
+              else rs2[0] += pk[0] ^ pk[5] ^ pk[10] ^ pk[15];   // keep the values alive
+              // release tile B's first key tile when tile A is half way through its first exponentials: the two
+              // groups then stay about half a period apart (one in its MUFU phase, the other loading / reducing)
+              if (c == 1 && j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
             }
           }
+          if (kc <= 32 && j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // (short first tile)
+          float rs, rs_hi;
+          unpack_f32x2(add_f32x2(rs2[0], rs2[1]), rs, rs_hi);
+          rs += rs_hi;
           FA_TRACE(tb + 4);
           l_run += rs;
-          if (!(ABL & 2)) fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core (async proxy)
+          tmem_st_wait();
           tc_fence_before();          // order this thread's TMEM accesses before the MMA that accumulates into O_g
           __syncwarp();
           if (lane == 0) mbar_arrive(p_full(g));
@@ -358,22 +389,32 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, __half* __re
         tmem_ld_32x32(o_col + 32, *reinterpret_cast<uint32_t (*)[32]>(&t[32]));
         tmem_ld_wait();
         tc_fence_before();
-        const float inv = 1.0f / l_run;
-        const int tq = q0 + r;
-        if (tq < T) {   // each thread owns one full 128-byte output row
-          uint4* og = reinterpret_cast<uint4*>(out + (long long)(row0 + tq) * d + h * FA_D);
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(l_run));
+        // normalised [128 x 64] fp16 tile -> swizzled staging tile -> one TMA store (rows >= T are clipped by the
+        // 3D tensor map). The elected thread first makes sure the previous item's store has finished reading.
+        if (q == 0 && lane == 0) tma_store_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory");
+        const uint32_t srow = sO + g * FA_TILE + r * 128;
 #pragma unroll
-          for (int i = 0; i < FA_D; i += 8) {
-            uint4 wv;
-            wv.x = pack_half2(__uint_as_float(t[i + 0]) * inv, __uint_as_float(t[i + 1]) * inv);
-            wv.y = pack_half2(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
-            wv.z = pack_half2(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv);
-            wv.w = pack_half2(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv);
-            og[i >> 3] = wv;
-          }
+        for (int i = 0; i < FA_D; i += 8) {
+          const uint32_t w0 = pack_half2(__uint_as_float(t[i + 0]) * inv, __uint_as_float(t[i + 1]) * inv);
+          const uint32_t w1 = pack_half2(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
+          const uint32_t w2 = pack_half2(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv);
+          const uint32_t w3 = pack_half2(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((((i >> 3) ^ (r & 7))) << 4)), "r"(w0),
+                       "r"(w1), "r"(w2), "r"(w3)
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory");
+        if (q == 0 && lane == 0) {
+          tma_store_3d(&tmO, sO + g * FA_TILE, h * FA_D, q0, bh / heads);
+          tma_store_commit();
         }
       }
     }
+    if (q == 0 && lane == 0) tma_store_wait_all<0>();   // the staging tile must outlive the last store
   }
   tc_fence_before();
   __syncthreads();
@@ -389,12 +430,13 @@ int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cud
     DSS_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
 #ifdef DSS_ATTN_ABLATION
 #define DSS_ABL_ATTR(n) DSS_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-    DSS_ABL_ATTR(1) DSS_ABL_ATTR(2) DSS_ABL_ATTR(4) DSS_ABL_ATTR(8) DSS_ABL_ATTR(16) DSS_ABL_ATTR(32) DSS_ABL_ATTR(3) DSS_ABL_ATTR(7) DSS_ABL_ATTR(39) DSS_ABL_ATTR(24) DSS_ABL_ATTR(63) DSS_ABL_ATTR(64) DSS_ABL_ATTR(65) DSS_ABL_ATTR(127) DSS_ABL_ATTR(88)
+    DSS_ABL_ATTR(1) DSS_ABL_ATTR(2) DSS_ABL_ATTR(4) DSS_ABL_ATTR(8) DSS_ABL_ATTR(16) DSS_ABL_ATTR(32) DSS_ABL_ATTR(3) DSS_ABL_ATTR(7) DSS_ABL_ATTR(39) DSS_ABL_ATTR(24) DSS_ABL_ATTR(63) DSS_ABL_ATTR(64) DSS_ABL_ATTR(65) DSS_ABL_ATTR(127) DSS_ABL_ATTR(88) DSS_ABL_ATTR(256) DSS_ABL_ATTR(512) DSS_ABL_ATTR(768) DSS_ABL_ATTR(1024)
 #endif
   }
-  CUtensorMap tm;
+  CUtensorMap tm, tmO;
   int rc = make_tmap_f16(&tm, qkv, B * T, 3 * heads * FA_D, FA_BM);
   if (rc) return rc;
+  if ((rc = make_tmap_out3d_f16(&tmO, out, B, T, heads * FA_D))) return rc;
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
@@ -413,10 +455,10 @@ int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cud
     DSS_CHECK_CUDA(cudaMemset(trace_dev, 0, 16384 * sizeof(long long)));
     DSS_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace, &trace_dev, sizeof(trace_dev)));
   }
-#define DSS_ABL_CASE(n) case n: attention_tcgen05_kernel<n><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, reinterpret_cast<__half*>(out), T, heads, nq2, total); break;
+#define DSS_ABL_CASE(n) case n: attention_tcgen05_kernel<n><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total); break;
   switch (abl) {
-    DSS_ABL_CASE(1) DSS_ABL_CASE(2) DSS_ABL_CASE(4) DSS_ABL_CASE(8) DSS_ABL_CASE(16) DSS_ABL_CASE(32) DSS_ABL_CASE(3) DSS_ABL_CASE(7) DSS_ABL_CASE(39) DSS_ABL_CASE(24) DSS_ABL_CASE(63) DSS_ABL_CASE(64) DSS_ABL_CASE(65) DSS_ABL_CASE(127) DSS_ABL_CASE(88)
-    default: attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, reinterpret_cast<__half*>(out), T, heads, nq2, total);
+    DSS_ABL_CASE(1) DSS_ABL_CASE(2) DSS_ABL_CASE(4) DSS_ABL_CASE(8) DSS_ABL_CASE(16) DSS_ABL_CASE(32) DSS_ABL_CASE(3) DSS_ABL_CASE(7) DSS_ABL_CASE(39) DSS_ABL_CASE(24) DSS_ABL_CASE(63) DSS_ABL_CASE(64) DSS_ABL_CASE(65) DSS_ABL_CASE(127) DSS_ABL_CASE(88) DSS_ABL_CASE(256) DSS_ABL_CASE(512) DSS_ABL_CASE(768) DSS_ABL_CASE(1024)
+    default: attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total);
   }
   if (trace_path) {
     static long long host[16384];
@@ -426,7 +468,7 @@ int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cud
     if (f) { fwrite(host, sizeof(host), 1, f); fclose(f); }
   }
 #else
-  attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, reinterpret_cast<__half*>(out), T, heads, nq2, total);
+  attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total);
 #endif
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;

@@ -569,6 +569,26 @@ int make_tmap_out3d_f32(CUtensorMap* tm, const void* ptr, int images, int rows, 
   return DSS_OK;
 }
 
+// 3D fp16 output [images, rows, cols] written in 128-row x 64-column boxes (128 B swizzle); rows past `rows` of an image
+// are clipped by the TMA unit, so a partial last tile never spills into the next image.
+int make_tmap_out3d_f16(CUtensorMap* tm, const void* ptr, int images, int rows, int cols) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return DSS_ERR_CUDA;
+  DSS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cols % 64 == 0, "fp16 tile output must be 16-byte aligned, cols %% 64 == 0");
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)images};
+  cuuint64_t gstride[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3D fp16 output) failed with CUresult %d", (int)r);
+    return DSS_ERR_CUDA;
+  }
+  return DSS_OK;
+}
+
 template <int EPI, int BN, int ST = default_stages(BN, epi_uses_tma_store(EPI))>
 static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, int M, int N, int K,
                         const EpiParams& p, cudaStream_t st, int kclass, int batch) {
