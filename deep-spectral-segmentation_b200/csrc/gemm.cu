@@ -504,7 +504,8 @@ static PFN_encodeTiled get_encode_fn() {
 int gemm_tile_n(int N) {
   static const char* force = getenv("DSS_GEMM_BN");  // tuning override (experiments only)
   if (force) return atoi(force);
-  return N % 256 == 0 ? 256 : 128;
+  // widest tile that divides N: operand bytes per FLOP (shared-memory bandwidth, the binding resource) fall with BN
+  return N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128);
 }
 
 // 2D fp16 row-major [rows, cols] tensor, box = 64 columns x box_rows rows, 128 B swizzle, zero fill out of bounds.
@@ -633,6 +634,9 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      const EpiParams& p, cudaStream_t st, int kclass, int bn, int batch = 1) {
   switch (bn) {
     case 128: return launch_tc_bn<EPI, 128>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
+    case 192:
+      if constexpr (epi_uses_tma_store(EPI)) return launch_tc_bn<EPI, 192>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
+      break;
     case 256:
       if constexpr (epi_uses_tma_store(EPI)) return launch_tc_bn<EPI, 256>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
       break;
@@ -752,6 +756,7 @@ extern "C" int dss_debug_gemm_cfg(const void* A, const void* Wt, const float* bi
   switch (key) {
     case 1282: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 2>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
     case 1283: return launch_tc_bn<DSS_EPI_BIAS_F16, 128, 3>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
+    case 1924: return launch_tc_bn<DSS_EPI_BIAS_F16, 192, 4>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
     case 2563: return launch_tc_bn<DSS_EPI_BIAS_F16, 256, 3>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
     case 2564: return launch_tc_bn<DSS_EPI_BIAS_F16, 256, 4>(tmA, tmB, &tmC, M, N, K, p, st, KC_GEMM_OTHER, 1);
   }

@@ -6,7 +6,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 _lib = importlib.import_module("deep-spectral-segmentation_b200._lib")
 lib = _lib.load()
 dev = torch.device("cuda:0")
-M = 32 * 901
+M = 256 * 901
 def run(N, K, bn, st, iters=20):
     A = torch.randn(M, K, device=dev).half(); W = (torch.randn(N, K, device=dev) * 0.05).half()
     bias = torch.zeros(N, device=dev); out = torch.empty(M, N, device=dev, dtype=torch.float16)
@@ -25,6 +25,6 @@ def run(N, K, bn, st, iters=20):
     err = (out[:256].float() - ref).abs().max().item()
     print(f"N={N:5d} K={K:5d} bn={bn} stages={st}: {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TFLOP/s  err {err:.2e}")
 for (N, K) in [(1152, 384), (1536, 384), (384, 1536), (384, 384)]:
-    for bn, st in [(128, 3), (256, 4)]:
+    for bn, st in [(128, 3), (192, 4), (256, 4)]:
         if N % bn: continue
         run(N, K, bn, st)
