@@ -246,6 +246,9 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION in this image) to stdout by default; stdout carries the
+        # ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     # the one collective of the path: DINO weights from rank 0
     sd0 = vit.random_state_dict(args.model, 0) if rank == 0 else None
