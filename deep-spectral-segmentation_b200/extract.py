@@ -255,6 +255,75 @@ def extract_single_region_segmentations(features_dir: str, eigs_dir: str, output
                            multiprocessing)
 
 
+def _extract_multi_region_segmentations(inp, adaptive: bool, non_adaptive_num_segments: int, infer_bg_index: bool,
+                                        kmeans_baseline: bool, output_dir: str, num_eigenvectors: int,
+                                        random_state: Optional[int] = None):
+    """Worker with the reference's signature (extract.py:283-349): K-means on the non-constant eigenvectors (or on the
+    raw features, ``kmeans_baseline``) of one image -> label map on the patch grid, background label swapped to 0.
+
+    The clustering is scikit-learn's KMeans exactly as in the reference (unseeded there; ``random_state`` is an
+    extension, None = reference behaviour). It runs on the host: N <= a few thousand points in <= K dimensions.
+    """
+    from PIL import Image
+    from sklearn.cluster import KMeans
+    index, (feature_path, eigs_path) = inp
+    data_dict = torch.load(feature_path, map_location="cpu")
+    data_dict.update(torch.load(eigs_path, map_location="cpu", weights_only=False))
+    id = Path(data_dict["id"])
+    output_file = str(Path(output_dir) / f"{id}.png")
+    if Path(output_file).is_file():
+        print(f"Skipping existing file {str(output_file)}")
+        return
+    B, C, H, W, P, H_patch, W_patch, H_pad, W_pad = utils.get_image_sizes(data_dict)
+    if adaptive:   # number of segments = position of the largest eigengap (the gap after the constant vector excluded)
+        by_gap = np.argsort(np.diff(data_dict["eigenvalues"].numpy()))[::-1]
+        n_clusters = by_gap[by_gap != 0][0] + 1
+    else:
+        n_clusters = non_adaptive_num_segments
+    kmeans = KMeans(n_clusters=n_clusters) if random_state is None else KMeans(n_clusters=n_clusters,
+                                                                                random_state=random_state)
+    if kmeans_baseline:
+        clusters = kmeans.fit_predict(data_dict["k"].squeeze().numpy())
+    else:
+        clusters = kmeans.fit_predict(data_dict["eigenvectors"][1:1 + num_eigenvectors].numpy().T)
+    if clusters.size == H_patch * W_patch:
+        segmap = clusters.reshape(H_patch, W_patch)
+    elif clusters.size == H_patch * W_patch * 4:     # eigenvectors of the image_downsample_factor = P/2 mode
+        segmap = clusters.reshape(H_patch * 2, W_patch * 2)
+    else:
+        raise ValueError(f"{clusters.size} labels do not fit a {H_patch} x {W_patch} patch grid")
+    if infer_bg_index:   # the label owning most of the border becomes 0 (labels 0 and bg are swapped)
+        labels, share = utils.get_border_fraction(segmap)
+        bg_index = labels[np.argmax(share)].item()
+        bg_region, zero_region = segmap == bg_index, segmap == 0
+        segmap[bg_region] = 0
+        segmap[zero_region] = bg_index
+    Image.fromarray(segmap).convert("L").save(output_file)
+
+
+def extract_multi_region_segmentations(features_dir: str, eigs_dir: str, output_dir: str, adaptive: bool = False,
+                                       non_adaptive_num_segments: int = 4, infer_bg_index: bool = True,
+                                       kmeans_baseline: bool = False, num_eigenvectors: int = 1_000_000,
+                                       multiprocessing: int = 0, random_state: Optional[int] = None,
+                                       yes: Optional[bool] = None):
+    """
+    Second consumer of the eigs files, same command / file contract as the reference
+    (extract/extract.py:352-376).
+
+    Example:
+    python extract.py extract_multi_region_segmentations \
+        --features_dir "./data/VOC2012/features/dino_vits16" \
+        --eigs_dir "./data/VOC2012/eigs/laplacian" \
+        --output_dir "./data/VOC2012/multi_region_segmentation/fixed" \
+    """
+    utils.make_output_dir(output_dir, assume_yes=yes)
+    inputs = utils.get_paired_input_files(features_dir, eigs_dir)
+    utils.parallel_process(
+        inputs, lambda inp: _extract_multi_region_segmentations(inp, adaptive, non_adaptive_num_segments, infer_bg_index,
+                                                                kmeans_baseline, output_dir, num_eigenvectors,
+                                                                random_state), multiprocessing)
+
+
 def extract_all(images_list: str, images_root: Optional[str], model_name: str, features_dir: Optional[str],
                 eigs_dir: str, K: int = 20, batch_size: int = 16, which_block: int = -1, normalize: bool = True,
                 threshold_at_zero: bool = True, lapnorm: bool = True, image_color_lambda: float = 0.0,

@@ -91,6 +91,18 @@ def make_output_dir(output_dir, check_if_empty=True, assume_yes: Optional[bool] 
             sys.exit()
 
 
+def get_border_fraction(segmap: np.ndarray):
+    """extract_utils.py:124-135 restated: per label, its share of the 2(H+W) border cells (corners count twice)."""
+    labels = np.unique(segmap)
+    counts = {int(v): 0 for v in labels}
+    for edge in (segmap[:, 0], segmap[:, -1], segmap[0, :], segmap[-1, :]):
+        vals, n = np.unique(edge, return_counts=True)
+        for v, c in zip(vals.tolist(), n.tolist()):
+            counts[v] += c
+    perimeter = 2 * (segmap.shape[0] + segmap.shape[1])
+    return np.array(list(counts.keys())), np.array(list(counts.values())) / perimeter
+
+
 def parallel_process(inputs: Iterable, fn: Callable, multiprocessing: int = 0):
     """Serial driver with the reference's timing print. ``multiprocessing`` is accepted for CLI compatibility; the
     GPU path batches images inside each kernel instead of forking CPU workers."""

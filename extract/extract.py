@@ -18,5 +18,6 @@ if __name__ == "__main__":
         extract_features=_extract.extract_features,
         extract_eigs=_extract.extract_eigs,
         extract_single_region_segmentations=_extract.extract_single_region_segmentations,
+        extract_multi_region_segmentations=_extract.extract_multi_region_segmentations,
         extract_all=_extract.extract_all,
     ))
