@@ -268,7 +268,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         if (j == 0 && g == 1) asm volatile("bar.sync 3, 256;" ::: "memory");
         mbar_wait(s_full(g), m & 1);
         tc_fence_after();
-        const int tb = (warp - 4) * 1024 + (m < 120 ? m : 120) * 8;
+        [[maybe_unused]] const int tb = (warp - 4) * 1024 + (m < 120 ? m : 120) * 8;   // trace slot (ablation builds)
         FA_TRACE(tb + 0);
         if (!dead) {
           // one key tile, in four chunks of 32 key columns; only the last tile of a row of tiles can be short

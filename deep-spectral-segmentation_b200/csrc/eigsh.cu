@@ -131,12 +131,11 @@ lanczos_laplacian_kernel(EigParams p) {
     }
     __syncthreads();
     double part = 0.0;
-    int clamped = 0;
     for (int i = tid; i < Npad; i += EIG_THREADS) {
       float dg = 0.f;
       if (i < N) {
         dg = wv[i];
-        if (dg < 1e-12f) { dg = 1.0f; clamped = 1; }
+        if (dg < 1e-12f) dg = 1.0f;   // get_diagonal's threshold (extract_utils.py:218)
         part += (double)dg;
       }
       wv[i] = dg;
@@ -161,7 +160,6 @@ lanczos_laplacian_kernel(EigParams p) {
       xs[i] = 0.f; vcur[i] = 0.f;
     }
     __syncthreads();
-    (void)clamped;
 
     int n = 0;          // Lanczos steps done
     int converged = (Kw <= 0);
