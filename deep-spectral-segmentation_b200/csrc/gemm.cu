@@ -41,17 +41,20 @@ __host__ __device__ constexpr bool epi_uses_tma_store(int epi) {
          epi == DSS_EPI_BIAS_F32 || epi == EPI_AFFINITY_F32;
 }
 constexpr int default_stages(int bn, bool tma) { return tma ? (bn == 128 ? 3 : 4) : 2; }
-// The kernel is L2 -> SM bandwidth bound (~9.6 TB/s measured): a 128 x BN tile needs (128 + BN) * 128 B of operands
-// per 64-deep K slab, so wide tiles and a deep ring (bytes in flight) are what matter.
-template <int BN, bool TMA_OUT, int ST = default_stages(BN, TMA_OUT)> struct TileCfg {
+// Shared-memory bandwidth is what bounds the kernel: wide tiles and a deep ring are what matter.
+// CG = 1: one CTA per output tile, the pair shares the weight tile by TMA multicast (each CTA still holds all of it).
+// CG = 2 (EXPERIMENTAL, off unless DSS_GEMM_2CTA=1, not yet validated on hardware): tcgen05.mma.cta_group::2, each CTA
+// holds only ITS half of the weight tile, which halves the B operand traffic per FLOP; the smaller stages buy a deeper ring.
+template <int BN, bool TMA_OUT, int ST = default_stages(BN, TMA_OUT), int CG = 1> struct TileCfg {
   static constexpr int KS = slabs_per_stage(BN);
   static constexpr int A_TILE_BYTES = KS * A_ATOM_BYTES;
-  static constexpr int B_ATOM_BYTES = BN * BK * 2;
+  static constexpr int B_ATOM_BYTES = BN * BK * 2 / CG;   // CG = 2: BN/2 rows per CTA
   static constexpr int B_TILE_BYTES = KS * B_ATOM_BYTES;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;   // [A atom 0 | A atom 1 | B atom 0 | B atom 1]
-  static constexpr int STAGES = ST;
-  static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;   // two fp32 accumulators, power-of-two allocation
   static constexpr int STAGING_BYTES = TMA_OUT ? 2 * BOX_BYTES : 4 * STG_BYTES;
+  static constexpr int MAX_STAGES = (232448 - 1024 - 1024 - 256 - STAGING_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = CG == 1 ? ST : (MAX_STAGES > 8 ? 8 : MAX_STAGES);
+  static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;   // two fp32 accumulators, power-of-two allocation
   // ring | staging | barriers | alignment slack
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
 };
@@ -150,14 +153,15 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int pairs_m, int tiles_n
   return TileCoord{((rem / tiles_n) * 2 + rank) * BM, (rem % tiles_n) * BN, z};
 }
 
-template <int EPI, int BN, int ST = default_stages(BN, epi_uses_tma_store(EPI))>
+template <int EPI, int BN, int ST = default_stages(BN, epi_uses_tma_store(EPI)), int CG = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int pairs_m, int tiles_n,
                         int total_items, EpiParams p) {
-  using Cfg = TileCfg<BN, epi_uses_tma_store(EPI), ST>;
+  using Cfg = TileCfg<BN, epi_uses_tma_store(EPI), ST, CG>;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, TMEM_COLS = Cfg::TMEM_COLS;
   constexpr int KS = Cfg::KS, A_TILE_BYTES = Cfg::A_TILE_BYTES;
+  static_assert(CG == 1 || epi_uses_tma_store(EPI), "the CTA-pair MMA path is only wired to the TMA-store epilogues");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024 B alignment (the swizzle pattern is a function of address bits [7,10))
   const uint32_t raw = smem_u32(smem_raw);
@@ -186,17 +190,24 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     if constexpr (epi_uses_tma_store(EPI)) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 2);   // released by the MMA warps of BOTH CTAs (each writes into the other's slot)
+      // CG 1: released by the MMA warps of BOTH CTAs (each writes into the other's slot); CG 2: one multicast commit
+      mbar_init(empty_bar(s), CG == 1 ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), epi_uses_tma_store(EPI) ? EPI_WARPS : MANUAL_EPI_WARPS);
+      // CG 2: the issuing (even) CTA collects the "accumulator drained" arrivals of both CTAs' epilogue warps
+      mbar_init(tempty_bar(i), (epi_uses_tma_store(EPI) ? EPI_WARPS : MANUAL_EPI_WARPS) * CG);
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_addr, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 1) {
+      tmem_alloc(tmem_ptr_addr, TMEM_COLS);
+      tmem_relinquish();
+    } else {
+      tmem_alloc_cg2(tmem_ptr_addr, TMEM_COLS);
+      tmem_relinquish_cg2();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -228,23 +239,35 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             kbB[a] = ka[a] < 2 * p.perm_blocks ? ka[a] + p.perm_blocks : ka[a] - p.perm_blocks;
         }
         if (elect_one()) {
-          mbar_arrive_expect_tx(fb, STAGE_BYTES);
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(fb, STAGE_BYTES);
 #pragma unroll
-          for (int a = 0; a < KS; ++a) {
-            tma_load_2d(sa + a * A_ATOM_BYTES, &tmA, fb, ka[a] * BK, row_base + tc.m0);
-            // this CTA's half of the weight slab (box 64 x BN/2 rows), delivered to both CTAs of the pair
-            tma_load_2d_mc(sa + A_TILE_BYTES + a * Cfg::B_ATOM_BYTES + rank * (Cfg::B_ATOM_BYTES / 2), &tmB, fb,
-                           kbB[a] * BK, row_base + tc.n0 + rank * (BN / 2), (uint16_t)0x3);
+            for (int a = 0; a < KS; ++a) {
+              tma_load_2d(sa + a * A_ATOM_BYTES, &tmA, fb, ka[a] * BK, row_base + tc.m0);
+              // this CTA's half of the weight slab (box 64 x BN/2 rows), delivered to both CTAs of the pair
+              tma_load_2d_mc(sa + A_TILE_BYTES + a * Cfg::B_ATOM_BYTES + rank * (Cfg::B_ATOM_BYTES / 2), &tmB, fb,
+                             kbB[a] * BK, row_base + tc.n0 + rank * (BN / 2), (uint16_t)0x3);
+            }
+          } else {
+            // both CTAs' bytes are credited to the even CTA's barrier, which the issuing MMA warp waits on
+            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * STAGE_BYTES);
+#pragma unroll
+            for (int a = 0; a < KS; ++a) {
+              tma_load_2d_cg2(sa + a * A_ATOM_BYTES, &tmA, fb, ka[a] * BK, row_base + tc.m0);
+              tma_load_2d_cg2(sa + A_TILE_BYTES + a * Cfg::B_ATOM_BYTES, &tmB, fb, kbB[a] * BK,
+                              row_base + tc.n0 + rank * (BN / 2));   // only THIS CTA's half of the weight slab
+            }
           }
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (CG == 1 || rank == 0)) {
     // MMA issuer: the whole warp waits on the barriers, one elected lane issues. Descriptors are computed from
     // warp-uniform values OUTSIDE the elected region: at 64-128 tensor cycles per UMMA the issue cost matters.
-    constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    // (CG 2: only the even CTA issues; one instruction drives both CTAs' tensor cores, M = 256.)
+    constexpr uint32_t idesc = umma_idesc_f16(BM * CG, BN);
     const uint32_t ubase = __shfl_sync(0xffffffffu, base, 0);
     const uint32_t utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
     int s = 0, lt = 0;
@@ -268,18 +291,26 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
           for (int a = 0; a < KS; ++a)
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_f16_ss(acc, adesc + (uint64_t)(a * (A_ATOM_BYTES >> 4) + 2 * k),
-                          bdesc + (uint64_t)(a * (Cfg::B_ATOM_BYTES >> 4) + 2 * k), idesc, (kb | a | k) != 0 ? 1u : 0u);
-          umma_commit_mc(eb, (uint16_t)0x3);  // slot free (in this CTA) once these MMAs have consumed it
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t ad = adesc + (uint64_t)(a * (A_ATOM_BYTES >> 4) + 2 * k);
+              const uint64_t bd = bdesc + (uint64_t)(a * (Cfg::B_ATOM_BYTES >> 4) + 2 * k);
+              if constexpr (CG == 1) umma_f16_ss(acc, ad, bd, idesc, (kb | a | k) != 0 ? 1u : 0u);
+              else umma_f16_ss_cg2(acc, ad, bd, idesc, (kb | a | k) != 0 ? 1u : 0u);
+            }
+          // slot free once these MMAs have consumed it (CG 1: in this CTA, arriving in both; CG 2: in both CTAs)
+          if constexpr (CG == 1) umma_commit_mc(eb, (uint16_t)0x3);
+          else umma_commit_cg2_mc(eb, (uint16_t)0x3);
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      if (elect_one()) umma_commit(tfull_bar(buf));  // accumulator complete
+      if (elect_one()) {   // accumulator complete (CG 2: in both CTAs)
+        if constexpr (CG == 1) umma_commit(tfull_bar(buf));
+        else umma_commit_cg2_mc(tfull_bar(buf), (uint16_t)0x3);
+      }
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 2) {
     // epilogue: group g owns columns [g*BN/2, (g+1)*BN/2) of the tile; a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int ew = warp - 2;
     const int g = ew >> 2, wq = ew & 3;
@@ -322,7 +353,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (b == NBOX - 1) {  // this warp has read all of its TMEM: hand the accumulator back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (lane == 0) {
+              if constexpr (CG == 1) mbar_arrive(tempty_bar(buf));
+              else mbar_arrive_cluster(tempty_bar(buf), 0);   // the even CTA's MMA warp owns both accumulators' release
+            }
           }
           float x[W];
 #pragma unroll
@@ -455,7 +489,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // the peer may still multicast / arrive into this CTA's shared memory until it is done too
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    else tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -590,13 +627,13 @@ int make_tmap_out3d_f16(CUtensorMap* tm, const void* ptr, int images, int rows, 
   return DSS_OK;
 }
 
-template <int EPI, int BN, int ST = default_stages(BN, epi_uses_tma_store(EPI))>
+template <int EPI, int BN, int ST = default_stages(BN, epi_uses_tma_store(EPI)), int CG = 1>
 static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, int M, int N, int K,
                         const EpiParams& p, cudaStream_t st, int kclass, int batch) {
-  using Cfg = TileCfg<BN, epi_uses_tma_store(EPI), ST>;
+  using Cfg = TileCfg<BN, epi_uses_tma_store(EPI), ST, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<EPI, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<EPI, BN, ST, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
   }
@@ -622,7 +659,7 @@ static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DSS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_tcgen05_kernel<EPI, BN, ST>, tmA, tmB, tmC ? *tmC : tmA, M, N, K,
+  DSS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16_tcgen05_kernel<EPI, BN, ST, CG>, tmA, tmB, tmC ? *tmC : tmA, M, N, K,
                                     pairs_m, tiles_n, total, p));
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
@@ -632,6 +669,18 @@ static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 template <int EPI>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, int M, int N, int K,
                      const EpiParams& p, cudaStream_t st, int kclass, int bn, int batch = 1) {
+  // EXPERIMENTAL CTA-pair MMA (tcgen05.mma.cta_group::2), opt-in for tuning: DSS_GEMM_2CTA=1. Not the product path.
+  static const bool two_cta = [] { const char* e = getenv("DSS_GEMM_2CTA"); return e && atoi(e) != 0; }();
+  if constexpr (epi_uses_tma_store(EPI) && EPI != EPI_AFFINITY_F32) {
+    if (two_cta) {
+      constexpr int D = 0;   // stage count is derived from the shared-memory budget for CG = 2
+      switch (bn) {
+        case 128: return launch_tc_bn<EPI, 128, D, 2>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
+        case 192: return launch_tc_bn<EPI, 192, D, 2>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
+        case 256: return launch_tc_bn<EPI, 256, D, 2>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
+      }
+    }
+  }
   switch (bn) {
     case 128: return launch_tc_bn<EPI, 128>(tmA, tmB, tmC, M, N, K, p, st, kclass, batch);
     case 192:
