@@ -247,3 +247,27 @@ def test_attention_exp2_polynomial_constants():
     rel = np.abs(res.astype(np.float64) / ref - 1.0)
     assert rel.max() < 4e-6, rel.max()                    # far below the fp16 rounding of P (4.9e-4)
     assert np.all(res[x < -125] < 3e-38)                  # masked keys (-inf -> clamp) pack to an fp16 zero
+
+
+def test_gemm_gelu_erf_constants():
+    """The fc1 epilogue evaluates the exact-erf GELU with Abramowitz & Stegun 7.1.26 (csrc/gemm.cu, gelu_erf). Emulate
+    it in float32 with the constants parsed out of the kernel source against torch's erf GELU in float64."""
+    import re
+    src = (ROOT / "deep-spectral-segmentation_b200" / "csrc" / "gemm.cu").read_text()
+    body = src[src.index("float gelu_erf(float x)"):src.index("// Row of the output buffer that GEMM row m maps to")]
+    pcoef = float(re.search(r"fmaf\((0\.\d+)f, z, 1\.0f\)", body).group(1))
+    a = [float(v) for v in re.findall(r"(-?\d\.\d{9})f\b", body)]     # the five 9-decimal A&S coefficients
+    assert len(a) == 5, a                                   # a5, a4, a3, a2, a1 in Horner order
+    x = np.linspace(-12.0, 12.0, 480001).astype(np.float32)
+    z = (np.abs(x) * np.float32(0.7071067811865476)).astype(np.float32)
+    t = (np.float32(1.0) / (np.float32(pcoef) * z + np.float32(1.0))).astype(np.float32)
+    poly = (t * np.float32(a[0]) + np.float32(a[1])).astype(np.float32)
+    for k in range(2, 5):
+        poly = (t * poly + np.float32(a[k])).astype(np.float32)
+    q = (np.float32(0.5) * t * poly * np.exp(-(z * z)).astype(np.float32)).astype(np.float32)
+    phi = np.where(x >= 0, np.float32(1.0) - q, q).astype(np.float32)
+    got = (x * phi).astype(np.float64)
+    ref = torch.nn.functional.gelu(torch.from_numpy(x.astype(np.float64))).numpy()
+    err = np.abs(got - ref)
+    assert err.max() < 2e-6, err.max()                      # A&S bound 1.5e-7 on erfc, times |x| <= 12
+    assert np.all(err <= 1e-6 + 2.5e-4 * np.abs(ref))       # well inside the fp16 rounding of the stored value
