@@ -61,12 +61,12 @@ PROTOTYPES = {
     "dss_op_im2col_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dss_affinity_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dss_affinity": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p,
-                             c_size_t, c_void_p]),
+                             c_void_p, c_size_t, c_void_p]),
     "dss_knn_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dss_knn_color_counts": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dss_eigsh_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "dss_eigsh_laplacian": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dss_eigsh_laplacian": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dss_eigsh_topk": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p]),
     "dss_upsample_bilinear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

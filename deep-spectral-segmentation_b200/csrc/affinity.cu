@@ -15,7 +15,8 @@ namespace dss {
 
 int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
 int affinity_gemm_tc(const CUtensorMap& tmS, const CUtensorMap& tmS_half, int images, int Nimg, int d, float* Wout, int ldw,
-                     const unsigned int* img_max, const uint8_t* counts, float lambda, int threshold, cudaStream_t st);
+                     const unsigned int* img_max, const unsigned int* img_absmax, const uint8_t* counts, float lambda,
+                     int threshold, float* deg_part, int ld_part, cudaStream_t st);
 
 // per-image max |f| (only needed when the features are NOT normalised: they are pre-scaled by a power of two so
 // that fp16 cannot overflow; the scale cancels in W / max(W))
@@ -101,6 +102,27 @@ upsample_bilinear_kernel(const float* __restrict__ f, float* __restrict__ out, i
     o[c] = hy * (hx * p00[c] + lx * p01[c]) + ly * (hx * p10[c] + lx * p11[c]);
 }
 
+// D = W 1 from the per-tile partial sums of the symmetric affinity epilogue (gemm.cu), in a fixed order: row m of
+// row tile I receives the row sums of tiles (I, j >= I) [slots 4 j + slice] and the column sums of tiles (i < I, I)
+// [slots 4 tiles + 4 i + lane quarter].
+__global__ void __launch_bounds__(256)
+degree_reduce_kernel(const float* __restrict__ part, float* __restrict__ deg, int N, int tiles, int ld_part) {
+  const int z = blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= N) return;
+  const float* p = part + (long long)z * (8 * tiles) * ld_part + m;
+  const int I = m >> 7;
+  float s = 0.f;
+  for (int k = 4 * I; k < 4 * tiles; ++k) s += p[(long long)k * ld_part];
+  for (int k = 0; k < 4 * I; ++k) s += p[(long long)(4 * tiles + k) * ld_part];
+  deg[(long long)z * N + m] = s;
+}
+
+static size_t degpart_bytes(int B, int N) {
+  const int tiles = (N + 127) / 128;
+  return align_up((size_t)B * 8 * tiles * (tiles * 128) * sizeof(float), 1024);
+}
+
 static size_t split_bytes(int B, int N, int d) {
   const int dpad = (d + 63) / 64 * 64;
   return align_up((size_t)B * N * 3 * dpad * sizeof(__half) + 128 * 3 * dpad * sizeof(__half), 1024);  // + tile overrun
@@ -112,11 +134,13 @@ using namespace dss;
 
 extern "C" size_t dss_affinity_workspace_bytes(int B, int N, int d) {
   if (B <= 0 || N <= 0 || d <= 0) return 0;
-  return split_bytes(B, N, d) + 2 * align_up((size_t)B * sizeof(unsigned int), 256);
+  return split_bytes(B, N, d) + 2 * align_up((size_t)B * sizeof(unsigned int), 256) + degpart_bytes(B, N) +
+         align_up((size_t)B * N * sizeof(float), 256);   // + degree output when the caller does not ask for it
 }
 
 extern "C" int dss_affinity(const float* feats, int B, int N, int d, int flags, const uint8_t* color_counts,
-                            float color_lambda, float* Wmat, int ldw, void* ws, size_t ws_bytes, dss_stream_t stream) {
+                            float color_lambda, float* Wmat, int ldw, float* degree, void* ws, size_t ws_bytes,
+                            dss_stream_t stream) {
   DSS_REQUIRE(feats && Wmat && ws, "affinity: null pointer");
   DSS_REQUIRE(B > 0 && N > 0 && d > 0, "affinity: empty problem B=%d N=%d d=%d", B, N, d);
   DSS_REQUIRE(ldw >= N && ldw % 4 == 0, "affinity: ldw must be >= N and a multiple of 4 (N=%d ldw=%d)", N, ldw);
@@ -148,8 +172,22 @@ extern "C" int dss_affinity(const float* feats, int B, int N, int d, int flags, 
   int rc = make_tmap_f16(&tmS, S, rows, 3 * dpad, 128);
   if (rc) return rc;
   if ((rc = make_tmap_f16(&tmS_half, S, rows, 3 * dpad, 64))) return rc;
-  return affinity_gemm_tc(tmS, tmS_half, B, N, dpad, Wmat, ldw, img_max, color_counts, color_lambda,
-                          ((flags & DSS_AFF_THRESHOLD_AT_ZERO) ? 1 : 0) | ((flags & DSS_AFF_NO_MAX_SCALE) ? 2 : 0), st);
+  const size_t flag_bytes = 2 * align_up((size_t)B * sizeof(unsigned int), 256);
+  float* deg_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + split_bytes(B, N, d) + flag_bytes);
+  float* deg_out = degree ? degree
+                          : reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(deg_part) + degpart_bytes(B, N));
+  const int tiles = (N + 127) / 128, ld_part = tiles * 128;
+  if ((rc = affinity_gemm_tc(tmS, tmS_half, B, N, dpad, Wmat, ldw, img_max, normalize ? nullptr : img_absmax, color_counts,
+                             color_lambda,
+                             ((flags & DSS_AFF_THRESHOLD_AT_ZERO) ? 1 : 0) | ((flags & DSS_AFF_NO_MAX_SCALE) ? 2 : 0),
+                             deg_part, ld_part, st)))
+    return rc;
+  {
+    LaunchScope scope(st, KC_ROWNORM);
+    degree_reduce_kernel<<<dim3(cdiv(N, 256), B), 256, 0, st>>>(deg_part, deg_out, N, tiles, ld_part);
+    DSS_CHECK_CUDA(cudaGetLastError());
+  }
+  return DSS_OK;
 }
 
 extern "C" int dss_normalize_rows(const float* feats, int rows, int d, float* out, dss_stream_t stream) {

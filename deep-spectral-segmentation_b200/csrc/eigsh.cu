@@ -8,9 +8,12 @@
 //
 // One persistent CTA per image: the whole iteration (mat-vec, re-orthogonalisation, Ritz extraction, convergence
 // test) runs inside one kernel with block-level barriers only; images are independent, so a batch fills the GPU
-// with one CTA (or more) per SM and nothing ever synchronises across CTAs. W (N^2 fp32, 3.2 MB at N=900) is
-// streamed once per mat-vec (L2-resident for typical batches); the Lanczos basis lives in a per-CTA global
-// scratch (L2), the working vectors in shared memory. Ritz values of the tridiagonal matrix come from a 32-way
+// with one CTA (or more) per SM and nothing ever synchronises across CTAs. The mat-vec is the only HBM stream of the
+// kernel and W is symmetric, so only its UPPER TRIANGLE is read: row r contributes W[r, c >= r] x[c] to y[r] (warp
+// reduction) and W[r, c > r] x[r] to y[c] (per-lane column accumulators in registers, combined across warps through
+// shared memory once per mat-vec) -- 2 N^2 bytes per step instead of 4 N^2. The degree D = W 1 comes from the
+// affinity kernel's epilogue (dss_affinity) when the caller passes it; otherwise one extra pass computes it.
+// The Lanczos basis lives in a per-CTA global scratch (L2), the working vectors in shared memory. Ritz values of the tridiagonal matrix come from a 32-way
 // Sturm multisection in fp64 (one warp per eigenvalue), Ritz vectors from a twisted factorisation.
 #include <math.h>
 
@@ -22,8 +25,12 @@ constexpr int EIG_THREADS = 512;
 constexpr int EIG_WARPS = EIG_THREADS / 32;
 constexpr int EIG_MAX_K = 64;
 
+constexpr int EIG_STRIP_CH = 8;                    // float4 column chunks per lane and strip
+constexpr int EIG_STRIP = 32 * 4 * EIG_STRIP_CH;   // 1024 columns per strip
+
 struct EigParams {
   const float* W;     // [B, N, ldw]
+  const float* deg;   // [B, N] row sums of W (from the affinity epilogue) or null: computed here
   float* evals;       // [B, K]
   float* evecs;       // [B, K, N]
   int* info;          // [B, 4]
@@ -87,7 +94,10 @@ __host__ __device__ inline size_t eig_double_bytes(int mmax) {
   return nd * sizeof(double);
 }
 
-__global__ void __launch_bounds__(EIG_THREADS, 2)
+// R = rows per warp and pass of the mat-vec (R independent 128-bit loads in flight per lane), MINB = CTAs per SM the
+// register budget is sized for: <2, 2> for N <= 1024 (two images per SM), <4, 1> beyond.
+template <int R, int MINB>
+__global__ void __launch_bounds__(EIG_THREADS, MINB)
 lanczos_laplacian_kernel(EigParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int N = p.N, Npad = p.Npad, mmax = p.mmax, K = p.K, ldw = p.ldw;
@@ -107,7 +117,10 @@ lanczos_laplacian_kernel(EigParams p) {
   float* vcur = wv + Npad;                                   // [Npad] current Lanczos vector
   float* dsc = vcur + Npad;                                  // [Npad] D^-1/2 (lapnorm) or D (unnormalised)
   float* u0 = dsc + Npad;                                    // [Npad] deflated null vector (unit 2-norm)
-  float* coef = u0 + Npad;                                   // [mmax + 2]
+  float* ycol = u0 + Npad;                                   // [Npad] column part of the symmetric mat-vec
+  const int stripw = Npad < EIG_STRIP ? Npad : EIG_STRIP;
+  float* colbuf = ycol + Npad;                               // [EIG_WARPS][stripw] per-warp column accumulators
+  float* coef = colbuf + (size_t)EIG_WARPS * stripw;         // [mmax + 2]
   __shared__ int s_flag;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -119,15 +132,21 @@ lanczos_laplacian_kernel(EigParams p) {
     const float* W = p.W + (size_t)img * N * ldw;
     __syncthreads();
     // ---- degree D = W 1  (row_sum, extract_utils.py:217), clamp < 1e-12 -> 1 (:218)
-    for (int r = warp; r < N; r += EIG_WARPS) {
-      const float4* row = reinterpret_cast<const float4*>(W + (size_t)r * ldw);
-      float s0 = 0.f, s1 = 0.f;
-      for (int i = lane; i < (Npad >> 2); i += 32) {  // pad columns [N, Npad) are zero
-        const float4 v = __ldg(row + i);
-        s0 += v.x + v.y; s1 += v.z + v.w;
+    if (plain) {              // plain top-K mode: no degree
+      for (int i = tid; i < N; i += EIG_THREADS) wv[i] = 1.0f;
+    } else if (p.deg != nullptr) {   // accumulated by the affinity epilogue: no pass over W
+      for (int i = tid; i < N; i += EIG_THREADS) wv[i] = __ldg(p.deg + (size_t)img * N + i);
+    } else {
+      for (int r = warp; r < N; r += EIG_WARPS) {
+        const float4* row = reinterpret_cast<const float4*>(W + (size_t)r * ldw);
+        float s0 = 0.f, s1 = 0.f;
+        for (int i = lane; i < (Npad >> 2); i += 32) {  // pad columns [N, Npad) are zero
+          const float4 v = __ldg(row + i);
+          s0 += v.x + v.y; s1 += v.z + v.w;
+        }
+        const float s = warp_sum(s0 + s1);
+        if (lane == 0) wv[r] = s;
       }
-      const float s = warp_sum(s0 + s1);
-      if (lane == 0) wv[r] = s;
     }
     __syncthreads();
     double part = 0.0;
@@ -189,37 +208,94 @@ lanczos_laplacian_kernel(EigParams p) {
 
       double anorm = 1.0;
       for (int j = 0; j < mmax; ++j) {
-        // ---- mat-vec  w = S v  (lapnorm)   or   w = (W - D) v  (unnormalised: top of -(D-W))
-        for (int i = tid; i < Npad; i += EIG_THREADS) xs[i] = lapn ? dsc[i] * vcur[i] : vcur[i];
+        // ---- mat-vec  w = S v  (lapnorm)   or   w = (W - D) v  (unnormalised: top of -(D-W)), upper triangle of W only
+        for (int i = tid; i < Npad; i += EIG_THREADS) {
+          xs[i] = lapn ? dsc[i] * vcur[i] : vcur[i];
+          wv[i] = 0.f;   // row part, accumulated strip by strip by the warp that owns the row
+        }
         __syncthreads();
-        // four rows per warp and pass: 4 independent 128-bit loads in flight per lane (the mat-vec is a pure HBM / L2
-        // stream, memory-level parallelism is what sets its bandwidth)
-        for (int r = warp * 4; r < N; r += EIG_WARPS * 4) {
+        for (int s0 = 0; s0 < Npad; s0 += EIG_STRIP) {
+          const int s1 = min(Npad, s0 + EIG_STRIP);          // columns [s0, s1) of this strip
+          float4 colacc[EIG_STRIP_CH];
+#pragma unroll
+          for (int k = 0; k < EIG_STRIP_CH; ++k) colacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           const float4* x4 = reinterpret_cast<const float4*>(xs);
-          const float4* rowp[4];
-          float acc[4][2];
+          // R consecutive rows per warp and pass (r % R == 0, so their diagonal elements share one 4-column chunk)
+          for (int r = warp * R; r < N && r < s1; r += EIG_WARPS * R) {
+            const float4* rowp[R];
+            float xr[R], acc[R];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            rowp[q] = reinterpret_cast<const float4*>(W + (size_t)min(r + q, N - 1) * ldw);
-            acc[q][0] = acc[q][1] = 0.f;
-          }
-          for (int i = lane; i < (Npad >> 2); i += 32) {
-            const float4 x = x4[i];
-            float4 u[4];
+            for (int q = 0; q < R; ++q) {
+              const bool ok = r + q < N;
+              rowp[q] = reinterpret_cast<const float4*>(W + (size_t)(ok ? r + q : N - 1) * ldw);
+              xr[q] = ok ? xs[r + q] : 0.f;
+              acc[q] = 0.f;
+            }
+            const int chd = r >> 2;                          // chunk that holds the diagonal elements of these rows
 #pragma unroll
-            for (int q = 0; q < 4; ++q) u[q] = __ldg(rowp[q] + i);
+            for (int k = 0; k < EIG_STRIP_CH; ++k) {
+              const int ch = (s0 >> 2) + lane + 32 * k;      // this lane's k-th chunk of the strip: columns 4 ch .. 4 ch + 3
+              if (4 * ch < s1 && ch >= chd) {
+                const float4 x = x4[ch];
+                float4 u[R];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              acc[q][0] = fmaf(u[q].x, x.x, acc[q][0]); acc[q][1] = fmaf(u[q].y, x.y, acc[q][1]);
-              acc[q][0] = fmaf(u[q].z, x.z, acc[q][0]); acc[q][1] = fmaf(u[q].w, x.w, acc[q][1]);
+                for (int q = 0; q < R; ++q) u[q] = __ldg(rowp[q] + ch);
+                if (ch == chd) {                             // diagonal chunk: drop the elements left of the diagonal
+#pragma unroll
+                  for (int q = 0; q < R; ++q) {
+                    const int dq = (r + q) & 3;
+                    if (dq > 0) u[q].x = 0.f;
+                    if (dq > 1) u[q].y = 0.f;
+                    if (dq > 2) u[q].z = 0.f;
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                  acc[q] = fmaf(u[q].x, x.x, acc[q]); acc[q] = fmaf(u[q].y, x.y, acc[q]);
+                  acc[q] = fmaf(u[q].z, x.z, acc[q]); acc[q] = fmaf(u[q].w, x.w, acc[q]);
+                }
+                if (ch == chd) {                             // the diagonal itself belongs to the row part only
+#pragma unroll
+                  for (int q = 0; q < R; ++q) {
+                    const int dq = (r + q) & 3;
+                    if (dq == 0) u[q].x = 0.f;
+                    if (dq == 1) u[q].y = 0.f;
+                    if (dq == 2) u[q].z = 0.f;
+                    if (dq == 3) u[q].w = 0.f;
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                  colacc[k].x = fmaf(u[q].x, xr[q], colacc[k].x); colacc[k].y = fmaf(u[q].y, xr[q], colacc[k].y);
+                  colacc[k].z = fmaf(u[q].z, xr[q], colacc[k].z); colacc[k].w = fmaf(u[q].w, xr[q], colacc[k].w);
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+              const float sa = warp_sum(acc[q]);
+              if (lane == 0 && r + q < N) wv[r + q] += sa;   // row r is owned by this warp in every strip
             }
           }
+          // column part of the strip: per-warp accumulators -> shared memory -> summed in warp order (deterministic)
+          float4* cb = reinterpret_cast<float4*>(colbuf + (size_t)warp * stripw);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float sa = warp_sum(acc[q][0] + acc[q][1]);
-            if (lane == 0 && r + q < N)
-              wv[r + q] = lapn ? dsc[r + q] * sa : (plain ? sa : sa - dsc[r + q] * xs[r + q]);
+          for (int k = 0; k < EIG_STRIP_CH; ++k) {
+            const int cl = lane + 32 * k;                    // chunk inside the strip
+            if (4 * cl < s1 - s0) cb[cl] = colacc[k];
           }
+          __syncthreads();
+          for (int c = tid; c < s1 - s0; c += EIG_THREADS) {
+            float sc = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < EIG_WARPS; ++w2) sc += colbuf[(size_t)w2 * stripw + c];
+            ycol[s0 + c] = sc;
+          }
+          __syncthreads();
+        }
+        for (int i = tid; i < Npad; i += EIG_THREADS) {
+          const float sa = wv[i] + ycol[i];
+          wv[i] = (i < N) ? (lapn ? dsc[i] * sa : (plain ? sa : sa - dsc[i] * xs[i])) : 0.f;
         }
         __syncthreads();
         // ---- full re-orthogonalisation (CGS2) against u0, v_0..v_j ; alpha_j = sum of the v_j coefficients
@@ -429,7 +505,9 @@ lanczos_laplacian_kernel(EigParams p) {
 }
 
 static size_t eig_smem_bytes(int Npad, int mmax) {
-  return eig_double_bytes(mmax) + (size_t)5 * Npad * sizeof(float) + (size_t)(mmax + 2) * sizeof(float) + 16;
+  const int stripw = Npad < EIG_STRIP ? Npad : EIG_STRIP;
+  return eig_double_bytes(mmax) + (size_t)6 * Npad * sizeof(float) + (size_t)EIG_WARPS * stripw * sizeof(float) +
+         (size_t)(mmax + 2) * sizeof(float) + 16;
 }
 
 static int eig_resolve(int N, int K, int max_steps) {
@@ -446,6 +524,7 @@ static int eig_grid(int B, int Npad, int mmax) {
   const size_t smem = eig_smem_bytes(Npad, mmax);
   int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);  // 512 threads, <=64 regs => at most 2 CTAs / SM
+  if (Npad > EIG_STRIP) per_sm = 1;                     // the large-N instantiation is built for one CTA per SM
   int g = sms * per_sm;
   return B < g ? B : g;
 }
@@ -464,7 +543,7 @@ extern "C" size_t dss_eigsh_workspace_bytes(int B, int N, int K, int max_steps) 
   return basis + tri;
 }
 
-static int eigsh_launch(const float* Wmat, int ldw, int B, int N, int K, int mode, float tol, int max_steps,
+static int eigsh_launch(const float* Wmat, const float* deg, int ldw, int B, int N, int K, int mode, float tol, int max_steps,
                         float* evals, float* evecs, int* info, float* resid, void* ws, size_t ws_bytes,
                         dss_stream_t stream) {
   DSS_REQUIRE(Wmat && evals && evecs && info && ws, "eigsh: null pointer");
@@ -479,7 +558,7 @@ static int eigsh_launch(const float* Wmat, int ldw, int B, int N, int K, int mod
     return DSS_ERR_WORKSPACE;
   }
   EigParams p;
-  p.W = Wmat; p.evals = evals; p.evecs = evecs; p.info = info; p.resid = resid;
+  p.W = Wmat; p.deg = deg; p.evals = evals; p.evecs = evecs; p.info = info; p.resid = resid;
   p.B = B; p.N = N; p.ldw = ldw; p.Npad = (N + 3) & ~3; p.K = K; p.mode = mode;
   p.mmax = eig_resolve(N, K, max_steps);
   p.tol = tol > 0.f ? tol : 1e-6f;
@@ -492,20 +571,26 @@ static int eigsh_launch(const float* Wmat, int ldw, int B, int N, int K, int mod
     set_error("eigsh: N=%d with max_steps=%d needs %zu B of shared memory (> 227 KB)", N, p.mmax, smem);
     return DSS_ERR_UNSUPPORTED;
   }
-  DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchScope scope(static_cast<cudaStream_t>(stream), KC_EIGSH);
-  lanczos_laplacian_kernel<<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (p.Npad <= EIG_STRIP) {
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lanczos_laplacian_kernel<2, 2><<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lanczos_laplacian_kernel<4, 1><<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  }
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
 }
 
-extern "C" int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int K, int lapnorm, float tol,
-                                   int max_steps, float* evals, float* evecs, int* info, float* resid, void* ws,
-                                   size_t ws_bytes, dss_stream_t stream) {
-  return eigsh_launch(Wmat, ldw, B, N, K, lapnorm ? 0 : 1, tol, max_steps, evals, evecs, info, resid, ws, ws_bytes, stream);
+extern "C" int dss_eigsh_laplacian(const float* Wmat, const float* degree, int ldw, int B, int N, int K, int lapnorm,
+                                   float tol, int max_steps, float* evals, float* evecs, int* info, float* resid,
+                                   void* ws, size_t ws_bytes, dss_stream_t stream) {
+  return eigsh_launch(Wmat, degree, ldw, B, N, K, lapnorm ? 0 : 1, tol, max_steps, evals, evecs, info, resid, ws, ws_bytes,
+                      stream);
 }
 
 extern "C" int dss_eigsh_topk(const float* Amat, int lda, int B, int N, int K, float tol, int max_steps, float* evals,
                               float* evecs, int* info, float* resid, void* ws, size_t ws_bytes, dss_stream_t stream) {
-  return eigsh_launch(Amat, lda, B, N, K, 2, tol, max_steps, evals, evecs, info, resid, ws, ws_bytes, stream);
+  return eigsh_launch(Amat, nullptr, lda, B, N, K, 2, tol, max_steps, evals, evecs, info, resid, ws, ws_bytes, stream);
 }

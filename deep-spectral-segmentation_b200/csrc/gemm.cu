@@ -70,27 +70,60 @@ struct EpiParams {
   int batch_rows;
   // affinity epilogue
   const unsigned int* img_max;  // [images] float bits of max(W) per image
+  const unsigned int* img_absmax;  // [images] float bits of max|f| when the features were pre-scaled by 2^-e (else null)
   const uint8_t* counts;        // [images, M, M] colour-KNN counts or null
   float lambda;
   int threshold;                // bit 0: relu threshold, bit 1: do not divide by max(W)
   int perm_blocks;              // B operand K-slab permutation for the split-fp16 Gram product (0 = none)
+  // symmetric (affinity) mode: only tiles on or above the diagonal are computed; each strictly-upper tile is also
+  // stored transposed, and per-tile row / column sums go to deg_part [images, 2 * 4 * tiles, ld_part] (degree fusion)
+  int tri;
+  float* deg_part;
+  int ld_part;
 };
 
-// Exact-erf GELU x * Phi(x), branch-free. erfc via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, three orders of
-// magnitude below the fp16 rounding of the value this feeds): for z = |x|/sqrt(2),
-//   q = 0.5 * erfc(z) = 0.5 * t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + 0.3275911 z)
-// and Phi(x) = 1 - q for x >= 0, q for x < 0 (no cancellation on the negative side).
+// Exact-erf GELU x * Phi(x), Phi(x) = 0.5 + 0.5 erf(x / sqrt 2), branch-free and entirely on the FMA pipe (no MUFU):
+//   u = clamp(x / sqrt 2, -3, 3),  erf(u) ~= u P(u^2),  P = degree-8 minimax polynomial with the constraint 3 P(9) = 1
+// (so the clamped tails give Phi = 0 / 1 up to rounding). |erf error| <= 2.2e-5 -> |gelu error| <= 5.5e-5 absolute over
+// the whole fp32 range (tests/test_cpu_oracle.py evaluates this arithmetic in float32 against torch's float64 GELU);
+// the value is then rounded to fp16 (relative 4.9e-4). The previous formulation (Abramowitz-Stegun 7.1.26: one MUFU.RCP
+// and one MUFU.EX2 per element, ~14 scalar FMA-pipe instructions) made the fc1 epilogue longer than the tile's MMAs:
+// ncu showed the XU pipe at 38 % against 27 % for the tensor pipe. This one is 6.5 packed FMA-pipe + 2 ALU-pipe
+// instructions per element.
+#define DSS_GELU_C0 1.1283442974090576f
+#define DSS_GELU_C1 -0.3756363093852997f
+#define DSS_GELU_C2 0.11151406913995743f
+#define DSS_GELU_C3 -0.02537871152162552f
+#define DSS_GELU_C4 0.004330660682171583f
+#define DSS_GELU_C5 -0.0005299976910464466f
+#define DSS_GELU_C6 4.3234955228399485e-05f
+#define DSS_GELU_C7 -2.078214947687229e-06f
+#define DSS_GELU_C8 4.413194432117962e-08f
+#define DSS_GELU_CLAMP 3.0f
+__device__ __forceinline__ void gelu_erf_x2(float x0, float x1, float& y0, float& y1) {
+  const uint64_t x = pack_f32x2(x0, x1);
+  float u0, u1;
+  unpack_f32x2(mul_f32x2(x, pack_f32x2(0.70710678118654752440f, 0.70710678118654752440f)), u0, u1);
+  u0 = fmaxf(fminf(u0, DSS_GELU_CLAMP), -DSS_GELU_CLAMP);
+  u1 = fmaxf(fminf(u1, DSS_GELU_CLAMP), -DSS_GELU_CLAMP);
+  const uint64_t u = pack_f32x2(u0, u1);
+  const uint64_t s = mul_f32x2(u, u);
+  uint64_t p = fma_f32x2(pack_f32x2(DSS_GELU_C8, DSS_GELU_C8), s, pack_f32x2(DSS_GELU_C7, DSS_GELU_C7));
+  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C6, DSS_GELU_C6));
+  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C5, DSS_GELU_C5));
+  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C4, DSS_GELU_C4));
+  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C3, DSS_GELU_C3));
+  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C2, DSS_GELU_C2));
+  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C1, DSS_GELU_C1));
+  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C0, DSS_GELU_C0));
+  const uint64_t e = mul_f32x2(u, p);                                              // erf(x / sqrt 2)
+  const uint64_t phi = fma_f32x2(e, pack_f32x2(0.5f, 0.5f), pack_f32x2(0.5f, 0.5f));
+  unpack_f32x2(mul_f32x2(x, phi), y0, y1);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;  // MUFU.RCP (1 ulp); __frcp_rn would add a refinement step and a divergent special-case call per element
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  const float q = 0.5f * t * poly * __expf(-z * z);
-  const float phi = x >= 0.f ? 1.0f - q : q;
-  return x * phi;
+  float y0, y1;
+  gelu_erf_x2(x, x, y0, y1);
+  return y0;
 }
 
 // Row of the output buffer that GEMM row m maps to (or -1: skip).
@@ -147,7 +180,21 @@ __device__ __forceinline__ void epilogue_store(const float (&v)[32], int m, int 
 struct TileCoord { int m0, n0, z; };
 // work item t of a cluster = (image z, pair of vertically adjacent m-tiles, n-tile); CTA `rank` takes tile 2*pair+rank
 template <int BN>
-__device__ __forceinline__ TileCoord decode_tile(int t, int pairs_m, int tiles_n, int rank) {
+__device__ __forceinline__ TileCoord decode_tile(int t, int pairs_m, int tiles_n, int rank, int tri = 0) {
+  if (tri) {
+    // symmetric output (BN == BM): row pair p only visits n-tiles j >= 2p. Tile (2p+1, 2p) of the odd CTA lies below the
+    // diagonal: it is computed (the pair runs in lock step on the shared B tile) but never stored.
+    int per_img = 0;
+    for (int p = 0; p < pairs_m; ++p) per_img += max(tiles_n - 2 * p, 0);
+    const int z = t / per_img;
+    int rem = t - z * per_img, p = 0;
+    for (; p < pairs_m; ++p) {
+      const int cnt = max(tiles_n - 2 * p, 0);
+      if (rem < cnt) break;
+      rem -= cnt;
+    }
+    return TileCoord{(2 * p + rank) * BM, (2 * p + rem) * BN, z};
+  }
   const int per_img = pairs_m * tiles_n;
   const int z = t / per_img, rem = t - z * per_img;
   return TileCoord{((rem / tiles_n) * 2 + rank) * BM, (rem % tiles_n) * BN, z};
@@ -222,7 +269,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     int s = 0;
     uint32_t ph = 0;   // ring position, carried across tiles (no division in the loop)
     for (int t = cid; t < total_items; t += ncl) {
-      const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank);
+      const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank, p.tri);
       const int row_base = tc.z * p.batch_rows;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(bar_base + 8u * (STAGES + s), ph ^ 1u);
@@ -329,8 +376,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const bool issuer = (ew == 0) && (lane == 0);
       const uint32_t stage_u32 = base + STAGES * STAGE_BYTES;
       int lt = 0, cc = 0;
+      [[maybe_unused]] float aff_rowsum = 0.f;       // affinity: this thread's row sum over the tile's columns
       for (int t = cid; t < total_items; t += ncl, ++lt) {
-        const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank);
+        const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank, p.tri);
         const int buf = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(tfull_bar(buf), aph);
@@ -338,7 +386,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll 1
         for (int b = 0; b < NBOX; ++b, ++cc) {
           const int nc = tc.n0 + b * BOXC;           // first global column of the box
-          const bool live = nc < N;
+          bool live = nc < N;
           float bias_r[W];                            // independent of the accumulator: issued before the TMEM wait
 #pragma unroll
           for (int j = 0; j < W; j += 4) {
@@ -360,23 +408,84 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           }
           float x[W];
 #pragma unroll
-          for (int e = 0; e < W; ++e) {
-            x[e] = __uint_as_float(r[e]) + bias_r[e];
-            if constexpr (EPI == DSS_EPI_BIAS_GELU_F16) x[e] = gelu_erf(x[e]);
+          for (int e = 0; e < W; e += 2) {
+            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])),
+                                   pack_f32x2(bias_r[e], bias_r[e + 1])), x[e], x[e + 1]);
+            if constexpr (EPI == DSS_EPI_BIAS_GELU_F16) gelu_erf_x2(x[e], x[e + 1], x[e], x[e + 1]);
           }
           if constexpr (EPI == EPI_AFFINITY_F32) {
             // W[z, m, n] = relu(acc) / max (+ lambda * counts); columns >= M (row-pitch padding) are zeros; rows >= M
             // are clipped by the per-image (3D) tensor map
             const int m = tc.m0 + row, n = nc + sl * W;
             const float mx = __uint_as_float(__ldg(p.img_max + tc.z));
+            // un-normalised features were pre-scaled by pre = 2^-ceil(log2 max|f|) (affinity.cu): the scale cancels in
+            // W / max(W); when the division is skipped (which_matrix = 'affinity' / 'affinity_svd') it is undone here
+            float unscale = 1.0f;
+            if ((p.threshold & 2) && p.img_absmax != nullptr) {
+              const float am = __uint_as_float(__ldg(p.img_absmax + tc.z));
+              if (am > 0.f) unscale = exp2f(2.0f * ceilf(log2f(am)));
+            }
             const uint8_t* cnt = (p.counts && m < M) ? p.counts + ((long long)tc.z * M + m) * M + n : nullptr;
 #pragma unroll
             for (int e = 0; e < W; ++e) {
               float y = x[e];
               if (p.threshold & 1) y = y > 0.f ? y : 0.f;   // W * (W > 0)
               if (!(p.threshold & 2)) y = y / mx;           // W / W.max()
+              else y *= unscale;
               if (cnt && n + e < M) y += static_cast<float>(cnt[e]) * p.lambda;   // + W_color * lambda
               x[e] = (n + e < M) ? y : 0.f;
+            }
+            if (p.tri) {
+              // ---- symmetric mode. The matrix is exactly symmetric by construction (the same value is written to
+              // (m, n) and (n, m)), only tiles on or above the diagonal do any work, and the degree D = W 1 that the
+              // eigensolver starts from (extract_utils.py:207-220) is accumulated here instead of by another pass
+              // over W: per-thread row sums and per-warp column sums go to fixed partial slots (deterministic order).
+              live = live && tc.m0 <= tc.n0;                 // the odd CTA's below-diagonal tile stores nothing
+              const bool upper = tc.m0 < tc.n0;
+              const bool rowok = m < M;
+              if (b == 0) aff_rowsum = 0.f;
+              float xm[W];
+#pragma unroll
+              for (int e = 0; e < W; ++e) {
+                xm[e] = rowok ? x[e] : 0.f;
+                aff_rowsum += xm[e];
+              }
+              float* part = p.deg_part + (long long)tc.z * (8 * tiles_n) * p.ld_part;
+              if (upper) {
+                // mirrored store W[z, n + e, m] = W[z, m, n + e]: lanes hold consecutive m -> 128 B per warp store
+                float* Wz = reinterpret_cast<float*>(p.out) + (long long)tc.z * M * p.ldo;
+                if (m < p.ldo) {
+#pragma unroll
+                  for (int e = 0; e < W; ++e)
+                    if (n + e < M) Wz[(long long)(n + e) * p.ldo + m] = xm[e];
+                }
+                // column sums over this warp's 32 rows: segmented butterfly (8 -> 4 -> 2 -> 1 values per lane)
+                float c4[4], c2[2], c1;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float mine = (lane & 16) ? xm[e + 4] : xm[e], theirs = (lane & 16) ? xm[e] : xm[e + 4];
+                  c4[e] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const float mine = (lane & 8) ? c4[e + 2] : c4[e], theirs = (lane & 8) ? c4[e] : c4[e + 2];
+                  c2[e] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+                }
+                {
+                  const float mine = (lane & 4) ? c2[1] : c2[0], theirs = (lane & 4) ? c2[0] : c2[1];
+                  c1 = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+                }
+                c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+                c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
+                // lane l now holds the sum of column e = 4 * bit4 + 2 * bit3 + bit2 of l (all four lanes l & 3 agree)
+                if ((lane & 3) == 0) {
+                  const int e = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                  // column partial slot of (row tile i = m0 / BM, lane quarter q); it belongs to matrix row n + e
+                  part[(long long)(4 * tiles_n + (tc.m0 / BM) * 4 + q) * p.ld_part + n + e] = c1;
+                }
+              }
+              if (b == NBOX - 1 && tc.m0 <= tc.n0 && rowok)   // row partial slot of (column tile j, slice sl)
+                part[(long long)((tc.n0 / BN) * 4 + sl) * p.ld_part + m] = aff_rowsum;
             }
           }
           // the staging box is free once the store issued two boxes ago has finished READING it
@@ -419,7 +528,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     constexpr int NCHUNK = BN / 64;            // 32-column chunks per group
     int lt = 0, cc = 0;  // cc: running chunk counter -> consecutive chunks always use alternate staging buffers
     for (int t = cid; t < total_items; t += ncl, ++lt) {
-      const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank);
+      const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank, p.tri);
       const int buf = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       mbar_wait(tfull_bar(buf), aph);
@@ -638,7 +747,12 @@ static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     attr_set = true;
   }
   const int pairs_m = cdiv(cdiv(M, BM), 2), tiles_n = cdiv(N, BN);
-  const int total = pairs_m * tiles_n * batch;   // work items of a CTA pair
+  int per_img = pairs_m * tiles_n;
+  if (p.tri) {   // symmetric output: row pair p visits the n-tiles j >= 2p only (see decode_tile)
+    per_img = 0;
+    for (int q = 0; q < pairs_m; ++q) per_img += tiles_n - 2 * q > 0 ? tiles_n - 2 * q : 0;
+  }
+  const int total = per_img * batch;   // work items of a CTA pair
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
   const int clusters = total < sms / 2 ? total : sms / 2;
@@ -711,7 +825,7 @@ int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
                 int M, int N, int K, int epi, const float* aux, int rin, int rout, cudaStream_t st, int kclass, int bn) {
   int rc = check_gemm_args(M, N, K, epi, bias, out, aux, rin, rout);
   if (rc) return rc;
-  EpiParams p{out, bias, aux, N, rin, rout, 0, nullptr, nullptr, 0.f, 0, 0};
+  EpiParams p{out, bias, aux, N, rin, rout, 0, nullptr, nullptr, nullptr, 0.f, 0, 0, 0, nullptr, 0};
   switch (epi) {
     case DSS_EPI_BIAS_F16: return launch_tc<DSS_EPI_BIAS_F16>(tmA, tmB, tmC, M, N, K, p, st, kclass, bn);
     case DSS_EPI_BIAS_GELU_F16: return launch_tc<DSS_EPI_BIAS_GELU_F16>(tmA, tmB, tmC, M, N, K, p, st, kclass, bn);
@@ -727,10 +841,12 @@ int gemm_f16_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 // Batched Gram product for the affinity build: per image z, W[z] = epilogue(S[z] S'[z]^T) with S = split-fp16 rows
 // [images*Nimg, 3d] (see affinity.cu). N output columns cover the padded pitch ldw.
 int affinity_gemm_tc(const CUtensorMap& tmS, const CUtensorMap& tmS_half, int images, int Nimg, int d, float* Wout, int ldw,
-                     const unsigned int* img_max, const uint8_t* counts, float lambda, int threshold,
-                     cudaStream_t st) {
-  EpiParams p{Wout, nullptr, nullptr, ldw, 0, 0, Nimg, img_max, counts, lambda, threshold, d / BK};
+                     const unsigned int* img_max, const unsigned int* img_absmax, const uint8_t* counts, float lambda,
+                     int threshold, float* deg_part, int ld_part, cudaStream_t st) {
+  EpiParams p{Wout, nullptr, nullptr, ldw, 0, 0, Nimg, img_max, img_absmax, counts, lambda, threshold, d / BK,
+              1, deg_part, ld_part};
   DSS_REQUIRE(d % BK == 0, "affinity: feature dim must be a multiple of %d for the tensor-core path (got %d)", BK, d);
+  DSS_REQUIRE(deg_part != nullptr && ld_part >= cdiv(ldw, 128) * 128, "affinity: bad degree partial buffer");
   CUtensorMap tmW;
   int rc = make_tmap_out3d_f32(&tmW, Wout, images, Nimg, ldw);
   if (rc) return rc;
@@ -776,7 +892,7 @@ extern "C" int dss_op_gemm_f16_simt(const void* A, const void* Wt, const float* 
   int rc = check_gemm_args(M, N, K, epilogue, bias, out, aux, rin, rout);
   if (rc) return rc;
   DSS_REQUIRE(A && Wt, "gemm: null operand");
-  EpiParams p{out, bias, aux, N, rin, rout, 0, nullptr, nullptr, 0.f, 0, 0};
+  EpiParams p{out, bias, aux, N, rin, rout, 0, nullptr, nullptr, nullptr, 0.f, 0, 0, 0, nullptr, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epilogue) {
     case DSS_EPI_BIAS_F16: return launch_simt<DSS_EPI_BIAS_F16>(A, Wt, M, N, K, p, st);
@@ -799,7 +915,7 @@ extern "C" int dss_debug_gemm_cfg(const void* A, const void* Wt, const float* bi
   if ((rc = make_tmap_f16(&tmA, A, M, K, BM))) return rc;
   if ((rc = make_tmap_f16(&tmB, Wt, N, K, bn / 2))) return rc;
   if ((rc = make_tmap_out(&tmC, out, M, N, 0))) return rc;
-  EpiParams p{out, bias, nullptr, N, 0, 0, 0, nullptr, nullptr, 0.f, 0, 0};
+  EpiParams p{out, bias, nullptr, N, 0, 0, 0, nullptr, nullptr, nullptr, 0.f, 0, 0, 0, nullptr, 0};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int key = bn * 10 + stages;
   switch (key) {

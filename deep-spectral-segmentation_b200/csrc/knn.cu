@@ -51,9 +51,10 @@ knn_counts_kernel(const float* __restrict__ rgb, uint32_t* __restrict__ counts_w
   float q[5];
 #pragma unroll
   for (int c = 0; c < 5; ++c) q[c] = pts[c * N + qi];
-  uint32_t* cw = counts_words + ((size_t)b * N * N) / 4;  // host guarantees (B*N*N) % 4 == 0 per image via padding check
-  const size_t img_off_bytes = ((size_t)b * N * N) & 3;    // == 0 (checked on host)
-  (void)img_off_bytes;
+  // bytes are addressed over the WHOLE [B, N, N] buffer (only its base is 4-byte aligned), so odd N -- e.g. the 23 x 31
+  // grid of a 375 x 500 VOC image -- needs no row padding: byte e lives in word e >> 2 at bit offset 8 * (e & 3)
+  const size_t img_off = (size_t)b * N * N;
+  uint32_t* cw = counts_words;
   // last selected key (d2, idx); start below everything
   float last_d = -1.f;
   int last_j = -1;
@@ -75,7 +76,7 @@ knn_counts_kernel(const float* __restrict__ rgb, uint32_t* __restrict__ counts_w
     last_d = best_d;
     last_j = best_j;
     if (lane == 0 && best_j < N) {
-      const size_t e0 = (size_t)qi * N + best_j, e1 = (size_t)best_j * N + qi;
+      const size_t e0 = img_off + (size_t)qi * N + best_j, e1 = img_off + (size_t)best_j * N + qi;
       atomicAdd(cw + (e0 >> 2), 1u << (8 * (e0 & 3)));
       atomicAdd(cw + (e1 >> 2), 1u << (8 * (e1 & 3)));
     }
@@ -98,8 +99,7 @@ extern "C" int dss_knn_color_counts(const float* rgb, int B, int Hl, int Wl, uin
   DSS_REQUIRE(B > 0 && Hl > 0 && Wl > 0, "knn: empty problem");
   const int N = Hl * Wl;
   DSS_REQUIRE(N >= 20, "knn: need at least 20 points (k=20 neighbours), got %d", N);
-  DSS_REQUIRE(((size_t)N * N) % 4 == 0 && (reinterpret_cast<uintptr_t>(counts) & 3) == 0,
-              "knn: N*N must be a multiple of 4 and counts 4-byte aligned (N=%d)", N);
+  DSS_REQUIRE((reinterpret_cast<uintptr_t>(counts) & 3) == 0, "knn: counts must be 4-byte aligned");
   const size_t smem = (size_t)5 * N * sizeof(float);
   DSS_REQUIRE(smem <= 200 * 1024, "knn: N=%d points do not fit in shared memory", N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -34,7 +34,8 @@ def _feature_dict(k: torch.Tensor, index: int, file: str, model_name: str, patch
 
 
 def extract_features(images_list: str, images_root: Optional[str], model_name: str, batch_size: int, output_dir: str,
-                     which_block: int = -1, checkpoint: Optional[str] = None, seed: int = 0, yes: Optional[bool] = None):
+                     which_block: int = -1, checkpoint: Optional[str] = None, seed: Optional[int] = None,
+                     random_init: bool = False, yes: Optional[bool] = None):
     """
     Extract features from a list of images.
 
@@ -51,7 +52,8 @@ def extract_features(images_list: str, images_root: Optional[str], model_name: s
     if not ("dino" in model_name or "mocov3" in model_name):
         raise ValueError(model_name)
     dev = _device()
-    model, _, patch_size, _ = utils.get_model(model_name, checkpoint=checkpoint, seed=seed, device=dev)
+    model, _, patch_size, _ = utils.get_model(model_name, checkpoint=checkpoint, seed=seed, device=dev,
+                                              random_init=random_init)
     filenames = Path(images_list).read_text().splitlines()
     dataset = utils.ImagesDataset(filenames=filenames, images_root=images_root)
     print(f"Dataset size: {len(dataset)=}")

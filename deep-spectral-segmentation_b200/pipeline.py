@@ -88,8 +88,10 @@ class SpectralPipeline:
                 torch.cuda.current_stream(self.device).wait_event(events[i])
             self.model.forward_k(images_u8[s:s + vb], which_block=self.which_block, out=feats[s:s + vb])
         Wm = self._buf("W", (B, N, spectral.pitch(N)), torch.float32)
-        spectral.affinity(feats, self.normalize, self.threshold_at_zero, out=Wm)
-        evals, evecs, info, resid = spectral.eigsh_laplacian(Wm, N, self.K, self.lapnorm, self.tol, self.max_steps)
+        deg = self._buf("deg", (B, N), torch.float32)
+        spectral.affinity(feats, self.normalize, self.threshold_at_zero, out=Wm, degree=deg)
+        evals, evecs, info, resid = spectral.eigsh_laplacian(Wm, N, self.K, self.lapnorm, self.tol, self.max_steps,
+                                                             degree=deg)
         return evals, evecs, info
 
     @torch.no_grad()
@@ -167,4 +169,4 @@ class SpectralPipeline:
         """Kernels libdss_b200 launches for one run_device call (cross-checked against dss_kernel_launch_count)."""
         blk = which_block % depth
         vit = 3 + 7 * blk + 2
-        return n_vit_batches * vit + 2 + 1
+        return n_vit_batches * vit + 3 + 1   # rownorm/split, affinity GEMM, degree reduce; eigensolver

@@ -40,16 +40,19 @@ def knn_color_counts(rgb_lr: torch.Tensor, Hl: int, Wl: int) -> torch.Tensor:
     B, N, _ = rgb.shape
     assert N == Hl * Wl
     with torch.cuda.device(rgb.device):
-        counts = torch.empty(B, N, N, dtype=torch.uint8, device=rgb.device)
-        _lib.check(lib.dss_knn_color_counts(rgb.data_ptr(), B, Hl, Wl, counts.data_ptr(), None, 0,
+        # bytes are updated with 32-bit atomics: capacity rounded up to a whole word (any N, odd included)
+        flat = torch.empty((B * N * N + 3) // 4 * 4, dtype=torch.uint8, device=rgb.device)
+        _lib.check(lib.dss_knn_color_counts(rgb.data_ptr(), B, Hl, Wl, flat.data_ptr(), None, 0,
                                             _lib.stream_ptr(rgb.device)), "dss_knn_color_counts")
-    return counts
+    return flat[:B * N * N].view(B, N, N)
 
 
 @torch.no_grad()
 def affinity(feats: torch.Tensor, normalize=True, threshold_at_zero=True, color_counts: Optional[torch.Tensor] = None,
-             color_lambda: float = 0.0, out: Optional[torch.Tensor] = None, scale_by_max: bool = True) -> torch.Tensor:
-    """feats [B, N, d] fp32 CUDA -> W [B, N, pitch(N)] fp32 (columns >= N are zero)."""
+             color_lambda: float = 0.0, out: Optional[torch.Tensor] = None, scale_by_max: bool = True,
+             degree: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """feats [B, N, d] fp32 CUDA -> W [B, N, pitch(N)] fp32 (columns >= N are zero). If ``degree`` [B, N] fp32 is
+    given it receives the row sums of W, accumulated in the affinity kernel's epilogue (get_diagonal's row_sum)."""
     _lib.require_cuda(feats, "feats")
     lib = _lib.load()
     f = feats.to(torch.float32).contiguous()
@@ -67,15 +70,19 @@ def affinity(feats: torch.Tensor, normalize=True, threshold_at_zero=True, color_
         if color_counts is not None and color_lambda > 0:
             cc = color_counts.contiguous()
             assert cc.dtype == torch.uint8 and tuple(cc.shape) == (B, N, N)
+        if degree is not None:
+            assert degree.dtype == torch.float32 and degree.is_contiguous() and tuple(degree.shape) == (B, N)
         _lib.check(lib.dss_affinity(f.data_ptr(), B, N, d, flags, _lib.ptr(cc), float(color_lambda), out.data_ptr(), ldw,
-                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "dss_affinity")
+                                    _lib.ptr(degree), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "dss_affinity")
     return out
 
 
 @torch.no_grad()
-def eigsh_laplacian(W: torch.Tensor, N: int, K: int, lapnorm=True, tol: float = 0.0, max_steps: int = 0
+def eigsh_laplacian(W: torch.Tensor, N: int, K: int, lapnorm=True, tol: float = 0.0, max_steps: int = 0,
+                    degree: Optional[torch.Tensor] = None
                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-    """W [B, N, ldw] fp32 CUDA -> (eigenvalues [B,K], eigenvectors [B,K,N], info [B,4] int32, resid [B,K])."""
+    """W [B, N, ldw] fp32 CUDA (symmetric; the upper triangle is what is read) -> (eigenvalues [B,K], eigenvectors
+    [B,K,N], info [B,4] int32, resid [B,K]). ``degree`` [B, N]: row sums of W from affinity(), or None."""
     _lib.require_cuda(W, "W")
     lib = _lib.load()
     assert W.dtype == torch.float32 and W.is_contiguous() and W.dim() == 3 and W.shape[1] == N
@@ -88,7 +95,10 @@ def eigsh_laplacian(W: torch.Tensor, N: int, K: int, lapnorm=True, tol: float = 
         resid = torch.empty(B, K, dtype=torch.float32, device=dev)
         need = int(lib.dss_eigsh_workspace_bytes(B, N, K, max_steps))
         ws = _scratch.get("eig", need, dev)
-        _lib.check(lib.dss_eigsh_laplacian(W.data_ptr(), ldw, B, N, K, 1 if lapnorm else 0, float(tol), int(max_steps),
+        if degree is not None:
+            assert degree.dtype == torch.float32 and degree.is_contiguous() and tuple(degree.shape) == (B, N)
+        _lib.check(lib.dss_eigsh_laplacian(W.data_ptr(), _lib.ptr(degree), ldw, B, N, K, 1 if lapnorm else 0, float(tol),
+                                           int(max_steps),
                                            evals.data_ptr(), evecs.data_ptr(), info.data_ptr(), resid.data_ptr(),
                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "dss_eigsh_laplacian")
     return evals, evecs, info, resid
@@ -170,6 +180,7 @@ def laplacian_eigs(feats: torch.Tensor, K: int, normalize=True, threshold_at_zer
         if rgb_lr is None or lr_size is None:
             raise ValueError("image_color_lambda > 0 needs the low-resolution image (rgb_lr, lr_size)")
         cc = knn_color_counts(rgb_lr, lr_size[0], lr_size[1])
-    W = affinity(feats, normalize, threshold_at_zero, cc, color_lambda)
-    evals, evecs, info, resid = eigsh_laplacian(W, feats.shape[1], K, lapnorm, tol, max_steps)
+    deg = torch.empty(feats.shape[0], feats.shape[1], dtype=torch.float32, device=feats.device)
+    W = affinity(feats, normalize, threshold_at_zero, cc, color_lambda, degree=deg)
+    evals, evecs, info, resid = eigsh_laplacian(W, feats.shape[1], K, lapnorm, tol, max_steps, degree=deg)
     return evals, evecs, info, resid

@@ -171,19 +171,76 @@ def pos_embed_interp_host(pos_embed: torch.Tensor, grid0: int, Hp: int, Wp: int)
     return out
 
 
-def get_model(name: str, checkpoint: Optional[str] = None, seed: int = 0, device="cuda", state_dict=None):
+# upstream checkpoint file names (hubconf.py of facebookresearch/dino), looked up in the torch.hub cache
+HUB_FILES = {"dino_vits16": "dino_deitsmall16_pretrain.pth", "dino_vits8": "dino_deitsmall8_pretrain.pth",
+             "dino_vitb16": "dino_vitbase16_pretrain.pth", "dino_vitb8": "dino_vitbase8_pretrain.pth"}
+
+
+def clean_state_dict(sd: dict) -> Dict[str, torch.Tensor]:
+    """Accepts a backbone state_dict or a full DINO training checkpoint ({'teacher': ...}, 'module.' / 'backbone.'
+    prefixes, projection-head entries) and returns the backbone entries under the upstream names."""
+    for key in ("teacher", "state_dict", "model"):
+        if isinstance(sd, dict) and key in sd and isinstance(sd[key], dict):
+            sd = sd[key]
+    out = {}
+    for k, v in sd.items():
+        for prefix in ("module.", "backbone."):
+            if k.startswith(prefix):
+                k = k[len(prefix):]
+        if k.startswith("head."):
+            continue
+        out[k] = v
+    return out
+
+
+def find_checkpoint(name: str, checkpoint: Optional[str] = None) -> Optional[str]:
+    """Explicit path > $DSS_DINO_CHECKPOINT (a file, or a directory holding {name}.pth / the upstream file name) >
+    the torch.hub checkpoint cache (where torch.hub.load of the reference, extract_utils.py:42, leaves the weights)."""
+    import os
+    from pathlib import Path
+    if checkpoint:
+        return checkpoint
+    cands = []
+    env = os.environ.get("DSS_DINO_CHECKPOINT") or os.environ.get("DINO_CHECKPOINT")
+    if env:
+        e = Path(env)
+        cands += [e] if e.is_file() else [e / f"{name}.pth", e / HUB_FILES[name]]
+    try:
+        hub = Path(torch.hub.get_dir()) / "checkpoints"
+        cands.append(hub / HUB_FILES[name])
+    except Exception:
+        pass
+    for c in cands:
+        if c.is_file():
+            return str(c)
+    return None
+
+
+def get_model(name: str, checkpoint: Optional[str] = None, seed: Optional[int] = None, device="cuda", state_dict=None,
+              random_init: bool = False):
     """Mirror of utils.get_model (extract_utils.py:40-50): returns (model, val_transform, patch_size, num_heads).
 
     ``val_transform`` is None: ToTensor + Normalize are fused into the device im2col kernel, the model takes the
-    raw uint8 RGB image. Upstream weights come from ``checkpoint`` (a torch state_dict file with upstream names)
-    or, without one, from the upstream random-init recipe (no network in this environment)."""
+    raw uint8 RGB image. The reference downloads the pretrained DINO weights through torch.hub; here they come from
+    ``state_dict``, ``checkpoint``, $DSS_DINO_CHECKPOINT or the torch.hub cache (see find_checkpoint). Without any of
+    them the call RAISES -- features of a randomly initialised ViT under the name 'dino_vits16' would be garbage in
+    the reference's file layout -- unless the caller opts in with ``random_init=True`` or a ``seed`` (tests, benchmarks:
+    the upstream init recipe), which prints a loud warning."""
     name = name.lower()
     arch(name)
     if state_dict is None:
-        if checkpoint:
-            state_dict = torch.load(checkpoint, map_location="cpu")
-            state_dict = state_dict.get("state_dict", state_dict)
+        ckpt = find_checkpoint(name, checkpoint)
+        if ckpt:
+            state_dict = clean_state_dict(torch.load(ckpt, map_location="cpu"))
+        elif random_init or seed is not None:
+            import sys
+            print(f"WARNING: {name}: no pretrained checkpoint given or found -- using RANDOMLY INITIALISED weights "
+                  f"(seed {seed or 0}); the features are only meaningful for tests and benchmarks", file=sys.stderr)
+            state_dict = random_state_dict(name, seed or 0)
         else:
-            state_dict = random_state_dict(name, seed)
+            raise _lib.DssError(
+                f"{name}: pretrained DINO weights not found. The reference downloads them with torch.hub "
+                f"(extract_utils.py:42), which needs the network; pass checkpoint=<{HUB_FILES[name]}>, set "
+                "$DSS_DINO_CHECKPOINT, or opt into random weights with random_init=True / seed=<int> (tests only).")
     model = DinoViT(name, state_dict, device=device)
     return model, None, model.patch_size, model.num_heads

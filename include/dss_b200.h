@@ -152,19 +152,28 @@ size_t dss_affinity_workspace_bytes(int B, int N, int d);
  *   W  = F^ F^T ; W *= (W > 0) (if THRESHOLD) ; W /= max(W)                extract.py:191-194
  *        (NO_MAX_SCALE skips the division: the 'affinity' / 'affinity_svd' branches, extract.py:160-172)
  *   W += color_counts * color_lambda  (if color_counts != NULL)            extract.py:213,221
- * color_counts [B, N, N] uint8 is the dense KNN colour affinity of dss_knn_color_counts. */
+ *   degree[b, i] = sum_j W[b, i, j]   (if degree != NULL)                  extract_utils.py:217 (row_sum)
+ * color_counts [B, N, N] uint8 is the dense KNN colour affinity of dss_knn_color_counts.
+ * W is symmetric: only the tiles on or above the diagonal are computed on the tensor cores and each is stored twice
+ * (W[i,j] and W[j,i] are the same bits). The row sums are accumulated in the same epilogue (fixed summation order,
+ * bit-reproducible) so that the eigensolver does not need another pass over W; pass the result to
+ * dss_eigsh_laplacian. A colour term added AFTER this call (dss_rw_affinity_add) updates `degree` itself. */
 int dss_affinity(const float* feats, int B, int N, int d, int flags, const uint8_t* color_counts, float color_lambda,
-                 float* Wmat, int ldw, void* ws, size_t ws_bytes, dss_stream_t stream);
+                 float* Wmat, int ldw, float* degree, void* ws, size_t ws_bytes, dss_stream_t stream);
 
 /* Colour KNN affinity (extract_utils.py:151-188): rgb [B, Hl*Wl, 3] fp32 in [0,1] (the /255 low-res image of
  * extract.py:199-204). Two exact-KNN passes (k=20, w=2.0) and (k=10, w=0.1) over points (r,g,b,w*x,w*y),
  * x,y = linspace(0,1); counts[i,j] += 1 and counts[j,i] += 1 per directed neighbour pair (self included), i.e.
- * the dense form of the reference's duplicate-summing csr_matrix. counts [B, N, N] uint8 is overwritten. */
+ * the dense form of the reference's duplicate-summing csr_matrix. counts [B, N, N] uint8 is overwritten; the buffer
+ * must be 4-byte aligned and its capacity rounded up to a multiple of 4 bytes (bytes are updated with 32-bit atomics;
+ * any N, odd included). */
 size_t dss_knn_workspace_bytes(int B, int N);
 int dss_knn_color_counts(const float* rgb, int B, int Hl, int Wl, uint8_t* counts, void* ws, size_t ws_bytes,
                          dss_stream_t stream);
 
-/* Eigensolver. Wmat [B, N, ldw] symmetric, non-negative (row pitch ldw as written by dss_affinity).
+/* Eigensolver. Wmat [B, N, ldw] symmetric, non-negative (row pitch ldw as written by dss_affinity). Only the upper
+ * triangle (j >= i) of every matrix is read. degree [B, N] = row sums of W as written by dss_affinity, or NULL (the
+ * solver then computes them with one more pass over W).
  *   lapnorm != 0: K smallest pairs of (D - W) v = lambda D v, D = diag(rowsum W) (entries < 1e-12 -> 1,
  *                 extract_utils.py:217-218); eigenvectors D-orthonormal            extract.py:225-229
  *   lapnorm == 0: K smallest pairs of (D - W) v = lambda v, unit 2-norm vectors    extract.py:230-234
@@ -173,8 +182,8 @@ int dss_knn_color_counts(const float* rgb, int B, int Hl, int Wl, uint8_t* count
  * Method: Lanczos with full re-orthogonalisation on D^-1/2 W D^-1/2 (null vector deflated analytically), Ritz
  * values by Sturm bisection in fp64. tol <= 0 selects 1e-6; max_steps <= 0 selects min(N-1, 320). */
 size_t dss_eigsh_workspace_bytes(int B, int N, int K, int max_steps);
-int dss_eigsh_laplacian(const float* Wmat, int ldw, int B, int N, int K, int lapnorm, float tol, int max_steps,
-                        float* evals, float* evecs, int* info, float* resid, void* ws, size_t ws_bytes,
+int dss_eigsh_laplacian(const float* Wmat, const float* degree, int ldw, int B, int N, int K, int lapnorm, float tol,
+                        int max_steps, float* evals, float* evecs, int* info, float* resid, void* ws, size_t ws_bytes,
                         dss_stream_t stream);
 
 /* K algebraically largest eigenpairs of the symmetric matrices Amat [B, N, lda], descending, unit 2-norm vectors,

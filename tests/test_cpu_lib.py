@@ -31,14 +31,14 @@ def test_library_exports_every_declared_symbol():
 def test_bad_arguments_are_rejected_before_any_device_work():
     _lib = load_pkg("_lib")
     lib = _lib.load()
-    assert lib.dss_affinity(None, 1, 10, 8, 3, None, 0.0, None, 12, None, 0, None) == -1
+    assert lib.dss_affinity(None, 1, 10, 8, 3, None, 0.0, None, 12, None, None, 0, None) == -1
     assert b"null" in lib.dss_last_error()
     buf = torch.zeros(1 << 16, dtype=torch.uint8)
     p = (buf.data_ptr() + 255) // 256 * 256
-    assert lib.dss_affinity(p, 1, 10, 8, 3, None, 0.0, p, 11, p, 1 << 15, None) == -1      # ldw not multiple of 4
-    assert lib.dss_affinity(p, 1, 10, 8, 3, None, 0.0, p, 12, p, 16, None) == -3           # workspace too small
-    assert lib.dss_eigsh_laplacian(p, 12, 1, 10, 10, 1, 0.0, 0, p, p, p, None, p, 1 << 15, None) == -1   # K >= N
-    assert lib.dss_eigsh_laplacian(p, 12, 1, 10, 0, 1, 0.0, 0, p, p, p, None, p, 1 << 15, None) == -1    # K < 1
+    assert lib.dss_affinity(p, 1, 10, 8, 3, None, 0.0, p, 11, None, p, 1 << 15, None) == -1     # ldw not multiple of 4
+    assert lib.dss_affinity(p, 1, 10, 8, 3, None, 0.0, p, 12, None, p, 16, None) == -3         # workspace too small
+    assert lib.dss_eigsh_laplacian(p, None, 12, 1, 10, 10, 1, 0.0, 0, p, p, p, None, p, 1 << 15, None) == -1   # K >= N
+    assert lib.dss_eigsh_laplacian(p, None, 12, 1, 10, 0, 1, 0.0, 0, p, p, p, None, p, 1 << 15, None) == -1    # K < 1
     assert lib.dss_op_gemm_f16(p, p, p, p, 16, 30, 64, 0, None, 0, 0, None) == -1           # N % 32
     assert lib.dss_op_layernorm_f16(p, p, p, p, 4, 100, 1e-6, None) == -1                   # unsupported width
     cfg = _lib.VitConfig(16, 384, 12, 5, 4, 14, 1e-6)                                       # 384 / 5 != 64
@@ -75,14 +75,16 @@ def test_product_path_fails_loudly_without_cuda(tmp_path):
     spectral = load_pkg("spectral")
     ex = load_pkg("extract")
     with pytest.raises(_lib.DssError):
-        vit.get_model("dino_vits16", device="cpu")
+        vit.get_model("dino_vits16", device="cpu", seed=0)
+    with pytest.raises(_lib.DssError, match="pretrained DINO weights not found"):
+        vit.get_model("dino_vits16", device="cpu")          # no checkpoint and no explicit opt-in to random weights
     with pytest.raises(_lib.DssError):
         spectral.affinity(torch.zeros(1, 16, 8))
     with pytest.raises(_lib.DssError):
         spectral.eigsh_laplacian(torch.zeros(1, 16, 16), 16, 3)
     (tmp_path / "list.txt").write_text("a.jpg\n")
     with pytest.raises(_lib.DssError):
-        ex.extract_features(str(tmp_path / "list.txt"), str(tmp_path), "dino_vits16", 1, str(tmp_path / "out"))
+        ex.extract_features(str(tmp_path / "list.txt"), str(tmp_path), "dino_vits16", 1, str(tmp_path / "out"), seed=0)
     with pytest.raises(ValueError):
         vit.get_model("resnet50")
 
