@@ -6,6 +6,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+    python bench.py --workload c3|c4|c5 ...   # the other BASELINE.json configurations (one JSON line each)
 
 A step = one pass of the hot path over one batch of `--images-per-step` synthetic images per GPU (weak scaling).
 Rank 0 prints ONE JSON line. `value` is timed with the uint8 images already resident in HBM; `e2e` goes through
@@ -35,13 +36,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images-per-step", type=int, default=256)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = configs[1] (the metric's config, default); c3 = dino_vitb8 480px colour-KNN K=15; "
+                         "c4 = VOC-shaped variable sizes, dino_vits16 K=5; c5 = dino_vitb8 640px K=32 + N sweep")
+    ap.add_argument("--images-per-step", type=int, default=0,
+                    help="per GPU; 0 = workload default (c2: 296 = 2 x 148 SMs, c3: 16, c4: 592, c5: 4)")
     ap.add_argument("--size", type=int, default=480)
     ap.add_argument("--K", type=int, default=5)
     ap.add_argument("--model", default="dino_vits16")
     ap.add_argument("--vit-batch", type=int, default=0, help="images per ViT launch sequence (0 = the whole step)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images of the CPU-baseline sample (0 = 2 x workers)")
-    ap.add_argument("--parity-sample", type=int, default=4)
+    ap.add_argument("--parity-sample", type=int, default=64)
+    ap.add_argument("--no-as-shipped", action="store_true", help="skip the eager-GPU-ViT + CPU-eigsh baseline")
     ap.add_argument("--ref-images-per-step", type=int, default=0, help="0 = 2 x worker processes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -120,48 +126,27 @@ def load_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_images_per_sec(images_u8, model_name, K, sd, want_outputs=False):
-    """The reference's path on the host CPU (oracle port): fp32 eager DINO ViT + the reference's scipy eigsh route.
-    Returns (images/s, per-image outputs)."""
-    import torch
-    from oracle import dino_vit, eigs_ref
-    torch.set_grad_enabled(False)
-    ref = dino_vit.DinoViT(dino_vit.cfg_for(model_name)).eval()
-    ref.load_state_dict({k: v.float().cpu() for k, v in sd.items()})
-    P = ref.cfg.patch
-    outs = []
-    t0 = time.perf_counter()
-    t_vit = 0.0
-    for img in images_u8:
-        a = time.perf_counter()
-        k = ref.forward_k(dino_vit.preprocess_u8(img, P))
-        t_vit += time.perf_counter() - a
-        ev, vec = eigs_ref.extract_eig(k[0], K)
-        if want_outputs:
-            outs.append((k[0], ev, vec))
-    dt = time.perf_counter() - t0
-    return len(images_u8) / dt, outs, {"vit_s_per_image": t_vit / len(images_u8), "eigs_s_per_image": (dt - t_vit) / len(images_u8)}
-
-
-# ---- multi-process CPU arm: the reference's own parallel knob is a process pool over images
-# (extract_utils.py:138-148, `--multiprocessing N`); each worker runs the fp32 ViT + scipy eigsh route with a few
-# BLAS threads so that all host cores are busy.
+# CPU arms. The reference's own parallel knob is a process pool over images (extract_utils.py:138-148,
+# `--multiprocessing N`); each worker runs with a few BLAS threads so that all host cores are busy.
 _W = {}
 
 
-def _ref_worker_init(model_name, threads):
+def _ref_worker_init(model_name, threads, need_vit=True):
     import torch
     torch.set_num_threads(threads)
     torch.set_grad_enabled(False)
-    from oracle import dino_vit
-    vit = importlib.import_module(PKG + ".vit")
-    m = dino_vit.DinoViT(dino_vit.cfg_for(model_name)).eval()
-    m.load_state_dict(vit.random_state_dict(model_name, 0))
-    _W["model"] = m
+    if need_vit:
+        from oracle import dino_vit
+        vit = importlib.import_module(PKG + ".vit")
+        m = dino_vit.DinoViT(dino_vit.cfg_for(model_name)).eval()
+        m.load_state_dict(vit.random_state_dict(model_name, 0))
+        _W["model"] = m
 
 
 def _ref_worker_task(job):
-    seed, size, K = job
+    """One image through the reference's path on the CPU (oracle port): fp32 eager ViT + the scipy eigsh route.
+    job = (seed, size, K, want_outputs)."""
+    seed, size, K, want = job
     from oracle import dino_vit, eigs_ref
     synth = importlib.import_module(PKG + ".synth")
     m = _W["model"]
@@ -169,46 +154,147 @@ def _ref_worker_task(job):
     t0 = time.perf_counter()
     k = m.forward_k(dino_vit.preprocess_u8(img, m.cfg.patch))
     t1 = time.perf_counter()
-    eigs_ref.extract_eig(k[0], K)
-    return (t1 - t0, time.perf_counter() - t1)
+    st = {}
+    ev, vec = eigs_ref.extract_eig(k[0], K, stats=st)
+    t2 = time.perf_counter()
+    return (t1 - t0, t2 - t1, st.get("route"), (vec.numpy() if want else None))
 
 
-def cpu_pool_images_per_sec(model_name, size, K, n_images, steps, warmup, threads_per_worker=2):
-    """images/s of the CPU path with every host core busy: cores/threads_per_worker worker processes (2 threads per
-    worker measured best on the 2 x 32-core / 128-thread host of the B200 box: 9.3 img/s vs 7.6 at 4, 5.9 at 8)."""
-    import multiprocessing as mp
-    from concurrent.futures import ProcessPoolExecutor
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores // threads_per_worker, n_images, 64))
-    ctx = mp.get_context("spawn")
-    # numpy/scipy's BLAS (OpenBLAS) sizes its own thread pool from the environment at import time: without this
-    # every worker would start one BLAS thread per host core and the pool would thrash
-    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
-    for k in saved:
-        os.environ[k] = str(threads_per_worker)
-    try:
-        return _cpu_pool_run(ctx, workers, model_name, size, K, n_images, steps, warmup, threads_per_worker)
-    finally:
-        for k, v in saved.items():
+def _eigs_worker_task(job):
+    """Eigen stage of the reference on given features (the 1e-4 criterion is defined on identical features).
+    job = (path of an .npy with the (N, d) features, K, kwargs)."""
+    import numpy as np
+    import torch
+    from oracle import eigs_ref
+    path, K, kw = job
+    feats = torch.from_numpy(np.load(path))
+    st = {}
+    t0 = time.perf_counter()
+    ev, vec = eigs_ref.extract_eig(feats, K, stats=st, **kw)
+    return (time.perf_counter() - t0, st.get("route"), ev.numpy() if hasattr(ev, "numpy") else np.asarray(ev), vec.numpy())
+
+
+def _affinity_eigs_task(job):
+    """CPU half of the reference as shipped: W (already computed on the GPU, extract.py:191-195) -> degree + eigsh."""
+    import numpy as np
+    from oracle import eigs_ref
+    path, K = job
+    st = {}
+    eigs_ref.eigs_from_affinity(np.load(path), K, stats=st)
+    return (st["degree_s"], st["eigsh_s"], st["route"])
+
+
+class CpuPool:
+    """Process pool with every host core busy: cores / threads_per_worker workers (2 threads per worker measured best
+    on the 2 x 32-core / 128-thread host of the B200 box for the ViT + eigsh mix: 9.3 img/s vs 7.6 at 4, 5.9 at 8)."""
+
+    def __init__(self, model_name, threads_per_worker=2, max_workers=64, need_vit=True):
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        self.cores = os.cpu_count() or 1
+        self.threads = threads_per_worker
+        self.workers = max(1, min(self.cores // threads_per_worker, max_workers))
+        # numpy/scipy's BLAS (OpenBLAS) sizes its thread pool from the environment at import time: without this every
+        # worker would start one BLAS thread per host core and the pool would thrash
+        self._saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+        for k in self._saved:
+            os.environ[k] = str(threads_per_worker)
+        self.ex = ProcessPoolExecutor(self.workers, mp_context=mp.get_context("spawn"), initializer=_ref_worker_init,
+                                      initargs=(model_name, threads_per_worker, need_vit))
+
+    def map(self, fn, jobs, timeout=1200):
+        return list(self.ex.map(fn, jobs, timeout=timeout))
+
+    def close(self):
+        self.ex.shutdown()
+        for k, v in self._saved.items():
             if v is None:
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
 
+    def __enter__(self):
+        return self
 
-def _cpu_pool_run(ctx, workers, model_name, size, K, n_images, steps, warmup, threads_per_worker):
-    from concurrent.futures import ProcessPoolExecutor
-    with ProcessPoolExecutor(workers, mp_context=ctx, initializer=_ref_worker_init,
-                             initargs=(model_name, threads_per_worker)) as ex:
-        for w in range(max(1, warmup)):
-            list(ex.map(_ref_worker_task, [(10_000 + i, size, K) for i in range(workers)], timeout=600))
+    def __exit__(self, *a):
+        self.close()
+
+
+def cpu_pool_images_per_sec(model_name, size, K, n_images, steps, warmup):
+    with CpuPool(model_name) as pool:
+        for _ in range(max(1, warmup)):
+            pool.map(_ref_worker_task, [(10_000 + i, size, K, False) for i in range(pool.workers)])
         t0 = time.perf_counter()
         parts = []
         for s in range(steps):
-            parts += list(ex.map(_ref_worker_task, [(s * n_images + i, size, K) for i in range(n_images)], timeout=600))
+            parts += pool.map(_ref_worker_task, [(s * n_images + i, size, K, False) for i in range(n_images)])
         dt = time.perf_counter() - t0
-    split = {"vit_s_per_image": sum(p[0] for p in parts) / len(parts), "eigs_s_per_image": sum(p[1] for p in parts) / len(parts)}
-    return n_images * steps / dt, dt, {"workers": workers, "threads_per_worker": threads_per_worker, **split}
+        info = {"workers": pool.workers, "threads_per_worker": pool.threads,
+                "vit_s_per_image": sum(p[0] for p in parts) / len(parts),
+                "eigs_s_per_image": sum(p[1] for p in parts) / len(parts),
+                "sm_fallback_images": sum(1 for p in parts if p[2] == "SM-fallback"), "images": len(parts)}
+    return n_images * steps / dt, dt, info
+
+
+def as_shipped_baseline(model_name, size, K, n_images, dev):
+    """The reference AS SHIPPED on this box: extract_features = eager fp32 DINO ViT on the GPU
+    with batch size 1 (extract.py:71-114; the PyTorch restatement in oracle/dino_vit.py stands in for torch.hub's
+    model), then extract_eigs = GPU matmul for W, W.cpu(), and scipy eigsh on the host cores with the reference's own
+    knob (--multiprocessing <cores>, one BLAS thread per worker). The two commands run one after the other, so
+    images/s = 1 / (vit + affinity + eigs-pool time per image). Returns a dict with the per-image split."""
+    import numpy as np
+    import torch
+    from oracle import dino_vit
+    synth = importlib.import_module(PKG + ".synth")
+    vit = importlib.import_module(PKG + ".vit")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = dino_vit.DinoViT(dino_vit.cfg_for(model_name)).eval()
+    m.load_state_dict(vit.random_state_dict(model_name, 0))
+    m = m.to(dev)
+    P = m.cfg.patch
+    imgs = [synth.blobs_image(size, size, 50_000 + i) for i in range(n_images)]
+    xs = [dino_vit.preprocess_u8(im, P) for im in imgs]
+    for x in xs[:3]:
+        m.forward_k(x.to(dev))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    feats = [m.forward_k(x.to(dev, non_blocking=True)).cpu() for x in xs]       # H2D + forward + D2H, batch size 1
+    torch.cuda.synchronize()
+    t_vit = (time.perf_counter() - t0) / n_images
+    tmp = tempfile.mkdtemp(prefix="dss_asshipped_")
+    t0 = time.perf_counter()
+    paths = []
+    for i, f in enumerate(feats):                                                # extract.py:146-148,191-195
+        g = torch.nn.functional.normalize(f[0].to(dev), p=2, dim=-1)
+        W = g @ g.T
+        W = W * (W > 0)
+        W = (W / W.max()).cpu().numpy()
+        paths.append(os.path.join(tmp, f"w{i}.npy"))
+        np.save(paths[-1], W)
+    torch.cuda.synchronize()
+    t_aff = (time.perf_counter() - t0) / n_images
+    with CpuPool(model_name, threads_per_worker=1, max_workers=os.cpu_count() or 1, need_vit=False) as pool:
+        pool.map(_affinity_eigs_task, [(paths[i % n_images], K) for i in range(pool.workers)])     # warm-up
+        reps = max(1, (2 * pool.workers) // n_images)
+        jobs = [(p_, K) for _ in range(reps) for p_ in paths]
+        t0 = time.perf_counter()
+        parts = pool.map(_affinity_eigs_task, jobs)
+        t_eig = (time.perf_counter() - t0) / len(jobs)
+        workers = pool.workers
+    for p_ in paths:
+        os.unlink(p_)
+    os.rmdir(tmp)
+    per_image = t_vit + t_aff + t_eig
+    return {"value": 1.0 / per_image, "unit": "images/s",
+            "what": "reference as shipped: eager fp32 ViT on this GPU (batch 1) + GPU matmul + CPU scipy eigsh pool",
+            "per_image_ms": {"vit_gpu_eager_incl_copies": t_vit * 1e3, "affinity_gpu_plus_w_to_host_and_file": t_aff * 1e3,
+                             "degree_cpu_in_worker": 1e3 * sum(p_[0] for p_ in parts) / len(parts),
+                             "eigsh_cpu_in_worker": 1e3 * sum(p_[1] for p_ in parts) / len(parts),
+                             "eigs_stage_amortised_over_pool": t_eig * 1e3},
+            "eigs_pool": {"workers": workers, "threads_per_worker": 1, "images_per_s": 1.0 / t_eig,
+                          "sm_fallback": sum(1 for p_ in parts if p_[2] == "SM-fallback"), "jobs": len(parts)},
+            "sample": f"{n_images} synthetic {size}x{size} images"}
 
 
 def run_reference(args, rank):
@@ -217,215 +303,577 @@ def run_reference(args, rank):
     cores = os.cpu_count() or 1
     n = args.ref_images_per_step if args.ref_images_per_step > 0 else 2 * max(1, min(cores // 2, 64))
     value, dt, split = cpu_pool_images_per_sec(args.model, args.size, args.K, n, args.steps, args.warmup)
-    sample = (f"{n} synthetic {args.size}x{args.size} images per step (a bounded sample of the {args.images_per_step}-image step); "
+    sample = (f"{n} synthetic {args.size}x{args.size} images per step (a bounded sample of the step of the GPU arm); "
               f"fp32 eager DINO ViT + the reference's scipy eigsh route in {split['workers']} worker processes x "
               f"{split['threads_per_worker']} BLAS threads")
+    cb = {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample, "split": split}
+    try:
+        import torch
+        if torch.cuda.is_available() and not args.no_as_shipped:
+            cb["as_shipped"] = as_shipped_baseline(args.model, args.size, args.K, 32, torch.device("cuda:0"))
+    except Exception as e:  # noqa: BLE001   (the as-shipped leg is extra information, never the line's value)
+        cb["as_shipped"] = {"error": repr(e)}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[1]: {args.size}x{args.size} {args.model} dense affinity K={args.K}",
                        "images_per_step": n},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": sample, "split": split},
+            "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def run_ours(args, rank, local_rank, world):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    torch.set_grad_enabled(False)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a GPU: the hot path has no CPU fallback (use --impl reference for the CPU path)")
-    _lib = importlib.import_module(PKG + "._lib")
-    pipeline = importlib.import_module(PKG + ".pipeline")
-    synth = importlib.import_module(PKG + ".synth")
-    vit = importlib.import_module(PKG + ".vit")
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        # NCCL prints its version banner (NCCL_DEBUG=VERSION in this image) to stdout by default; stdout carries the
-        # ONE JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    # the one collective of the path: DINO weights from rank 0
-    sd0 = vit.random_state_dict(args.model, 0) if rank == 0 else None
-    sd = pipeline.broadcast_weights(args.model, 0, device=dev, src=0, state_dict=sd0)
-    if args.vit_batch <= 0:
-        args.vit_batch = args.images_per_step
-    pipe = pipeline.SpectralPipeline(args.model, K=args.K, device=dev, state_dict=sd, vit_batch=args.vit_batch)
-    P, d, depth = pipe.model.patch_size, pipe.model.dim, pipe.model.depth
-    B, S, K = args.images_per_step, args.size, args.K
-    N = (S // P) ** 2
-    T = N + 1
-    host_imgs = synth.blobs_batch(B, S, S, seed0=rank * B).pin_memory()
-    dev_imgs = host_imgs.to(dev)
-    torch.cuda.synchronize()
+class Ctx:
+    """Per-process state shared by the workloads: device, distributed helpers, model weights, clock sampler."""
 
-    def barrier():
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        torch.set_grad_enabled(False)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a GPU: the hot path has no CPU fallback (use --impl reference for the CPU path)")
+        self.args, self.rank, self.world, self.torch, self.dist = args, rank, world, torch, dist
+        self._lib = importlib.import_module(PKG + "._lib")
+        self.pipeline = importlib.import_module(PKG + ".pipeline")
+        self.spectral = importlib.import_module(PKG + ".spectral")
+        self.synth = importlib.import_module(PKG + ".synth")
+        self.vit = importlib.import_module(PKG + ".vit")
+        self.dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(self.dev)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            # NCCL prints its version banner (NCCL_DEBUG=VERSION in this image) to stdout by default; stdout carries the
+            # ONE JSON line only
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.sampler = ClockSampler(local_rank)
+        self.peaks = load_peaks()
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
+    def weights(self, model):
+        """the one collective of the path: DINO weights from rank 0"""
+        sd0 = self.vit.random_state_dict(model, 0) if self.rank == 0 else None
+        return self.pipeline.broadcast_weights(model, 0, device=self.dev, src=0, state_dict=sd0)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed(self, fn, steps, warmup):
+        """W untimed warm-ups, then exactly `steps` calls bracketed by barrier + synchronize; max over ranks (ms)."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        n0 = self._lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        self.sampler.mark_begin()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        self.sampler.mark_end()
+        return self.max_over_ranks(e0.elapsed_time(e1)), self._lib.launch_count() - n0
+
+    def profile(self, fn, steps):
+        """instrumented pass: CUDA events around every launch of the library"""
+        self._lib.profile(True)
+        for _ in range(steps):
+            fn()
+        self.torch.cuda.synchronize()
+        prof = self._lib.profile_read()
+        self._lib.profile(False)
+        return prof
+
+    def kernel_table(self, prof, alg):
+        kernels = []
+        total_ms = sum(v[1] for v in prof.values()) or 1.0
+        for name, (n_l, t_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            ent = {"kernel": name, "launches": n_l, "total_ms": round(t_ms, 4), "share": round(t_ms / total_ms, 4)}
+            if name in alg and n_l:
+                bound, work = alg[name]          # work = algorithmic FLOPs / bytes summed over the class's launches of ONE step
+                per_launch_s = t_ms / n_l * 1e-3
+                launches_per_step = n_l / max(1, self._prof_steps)
+                ach = work / launches_per_step / per_launch_s
+                if bound == "tensor":
+                    peak = self.peaks["tflops_sustained"]
+                    ent.update({"bound": "tensor", "achieved": round(ach / 1e12, 2), "peak": peak, "unit": "TFLOP/s",
+                                "frac": round(ach / 1e12 / peak, 4)})
+                else:
+                    peak = self.peaks["hbm_gbs"]
+                    ent.update({"bound": "hbm", "achieved": round(ach / 1e9, 1), "peak": peak, "unit": "GB/s",
+                                "frac": round(ach / 1e9 / peak, 4)})
+            kernels.append(ent)
+        return kernels
+
+    def roofline(self, kernels, traffic_lookup=None):
+        dom = next((k for k in kernels if "bound" in k), None)
+        if not dom:
+            return None
+        traffic = traffic_lookup(dom["kernel"]) if traffic_lookup else None
+        return {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "share_of_step": dom["share"],
+                "peak_source": self.peaks["source"] + (", sustained bf16 GEMM" if dom["bound"] == "tensor" else ""),
+                "timing": "CUDA events around every launch of the class in a separate instrumented pass of the same steps"}
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def vit_alg(P, d, depth_full, N, n_images):
+    """Algorithmic FLOPs of the ViT classes for n_images images: last block pruned to LN1 + K."""
+    T = N + 1
+    M = n_images * T
+    hid = 4 * d
+    L = depth_full
+    return {
+        "gemm_patch": ("tensor", 2.0 * n_images * N * (3 * P * P) * d),
+        "gemm_qkv": ("tensor", L * 2.0 * M * d * 3 * d),
+        "gemm_proj": ("tensor", L * 2.0 * M * d * d),
+        "gemm_fc1": ("tensor", L * 2.0 * M * d * hid),
+        "gemm_fc2": ("tensor", L * 2.0 * M * hid * d),
+        "gemm_kproj": ("tensor", 2.0 * M * d * d),
+        "attention": ("tensor", L * 4.0 * n_images * (d // 64) * T * T * 64),
+        "layernorm": ("hbm", (2 * L + 1) * M * d * (4 + 2)),
+        "im2col": ("hbm", n_images * (N * P * P * 3 + N * 3 * P * P * 2)),
+    }
+
+
+def eig_alg(B, N, d, K, m_steps, with_degree_pass=False):
+    """Affinity: read F once + write W once; eigensolver: the UPPER TRIANGLE of W once per Lanczos step (2 N^2 bytes,
+    csrc/eigsh.cu) + outputs. The degree comes from the affinity epilogue (no extra pass)."""
+    return {
+        "rownorm": ("hbm", B * N * d * (4 + 6)),
+        "affinity": ("hbm", B * (4.0 * N * d + 4.0 * N * N)),
+        "eigsh": ("hbm", B * (2.0 * N * (N + 1) * (m_steps + (1 if with_degree_pass else 0)) + 4.0 * K * N)),
+    }
+
+
+def load_traffic():
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = ROOT / "profiles" / name
+        if p.is_file():
+            try:
+                return json.loads(p.read_text()), name
+            except Exception:
+                pass
+    return None, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_c2(ctx: Ctx):
+    args, torch, dev = ctx.args, ctx.torch, ctx.dev
+    import numpy as np
+    sd = ctx.weights(args.model)
+    B = args.images_per_step or 296      # 2 x 148: the eigensolver (one CTA per image, two per SM) fills every SM slot
+    if args.vit_batch <= 0:
+        args.vit_batch = B
+    pipe = ctx.pipeline.SpectralPipeline(args.model, K=args.K, device=dev, state_dict=sd, vit_batch=args.vit_batch)
+    P, d, depth = pipe.model.patch_size, pipe.model.dim, pipe.model.depth
+    S, K = args.size, args.K
+    N = (S // P) ** 2
+    host_imgs = ctx.synth.blobs_batch(B, S, S, seed0=ctx.rank * B).pin_memory()
+    dev_imgs = host_imgs.to(dev)
+    torch.cuda.synchronize()
+    W, steps = max(args.warmup, 3), args.steps
+    ctx.sampler.start()
+
     # ---- device-resident throughput
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        pipe.run_device(dev_imgs)
-    barrier()
-    n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.mark_begin()
-    e0.record()
-    info = None
-    for _ in range(args.steps):
-        _, _, info = pipe.run_device(dev_imgs)
-    e1.record()
-    barrier()
-    sampler.mark_end()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - n0
-    value = world * B * args.steps / (ms * 1e-3)
+    last = {}
+
+    def step_dev():
+        last["out"] = pipe.run_device(dev_imgs)
+    ms, launches = ctx.timed(step_dev, steps, W)
+    value = ctx.world * B * steps / (ms * 1e-3)
+    info = last["out"][2]
     conv = int(info[:, 1].sum().item())
     steps_mean = float(info[:, 0].float().mean().item())
 
     # ---- end to end through the host-buffer call: every step copies its uint8 images from pinned host memory and
-    # brings the eigenvectors back; the streaming driver overlaps step i+1's H2D and step i-1's D2H with step i
-    for _ in pipe.run_host_pipelined([host_imgs] * 2):
+    # brings the features AND the eigenvectors back (what extract_features + extract_eigs deliver); the streaming
+    # driver overlaps step i+1's H2D and step i-1's D2H with step i
+    for _ in pipe.run_host_pipelined([host_imgs] * 2, features=True):
         pass
-    barrier()
-    sampler.mark_begin()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    ctx.sampler.mark_begin()
     e0.record()
     out = None
-    for out in pipe.run_host_pipelined([host_imgs] * args.steps):
+    for out in pipe.run_host_pipelined([host_imgs] * steps, features=True):
         pass
     e1.record()
-    barrier()
-    sampler.mark_end()
-    clocks = sampler.stop()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    ctx.barrier()
+    ctx.sampler.mark_end()
+    clocks = ctx.sampler.stop()
+    ms_e2e = ctx.max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = ctx.world * B * steps / (ms_e2e * 1e-3)
     h2d = int(host_imgs.numel())
-    d2h = int(out[0].numel() * 4 + out[1].numel() * 4 + out[2].numel() * 4)
+    d2h = int(sum(t.numel() * t.element_size() for t in out))
 
-    # ---- instrumented pass: CUDA events around every launch of the library, same K steps
-    _lib.profile(True)
-    for _ in range(args.steps):
-        pipe.run_device(dev_imgs)
-    torch.cuda.synchronize()
-    prof = _lib.profile_read()
-    _lib.profile(False)
-    peaks = load_peaks()
-    Mtok = args.vit_batch * T
-    hid = 4 * d
+    # ---- per-class device time and roofline fractions
+    ctx._prof_steps = steps
+    prof = ctx.profile(step_dev, steps)
     n_vit = (B + args.vit_batch - 1) // args.vit_batch
-    m_steps = steps_mean
-    # algorithmic work per launch: GEMM/attention FLOPs, affinity/eigsh bytes
-    alg = {
-        "gemm_patch": ("tensor", 2.0 * args.vit_batch * N * (3 * P * P) * d),
-        "gemm_qkv": ("tensor", 2.0 * Mtok * d * 3 * d),
-        "gemm_proj": ("tensor", 2.0 * Mtok * d * d),
-        "gemm_fc1": ("tensor", 2.0 * Mtok * d * hid),
-        "gemm_fc2": ("tensor", 2.0 * Mtok * hid * d),
-        "gemm_kproj": ("tensor", 2.0 * Mtok * d * d),
-        "attention": ("tensor", 4.0 * args.vit_batch * (d // 64) * T * T * 64),
-        "layernorm": ("hbm", Mtok * d * (4 + 2)),
-        "im2col": ("hbm", args.vit_batch * (S * S * 3 + N * 3 * P * P * 2)),
-        "rownorm": ("hbm", B * N * d * 8),
-        "affinity": ("hbm", B * (4.0 * N * d + 4.0 * N * N)),
-        "eigsh": ("hbm", B * (4.0 * N * N * (m_steps + 1) + 4.0 * K * N)),
-    }
-    kernels = []
-    total_ms = sum(v[1] for v in prof.values()) or 1.0
-    for name, (n_l, t_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-        ent = {"kernel": name, "launches": n_l, "total_ms": round(t_ms, 4), "share": round(t_ms / total_ms, 4)}
-        if name in alg and n_l:
-            bound, work = alg[name]
-            avg_s = t_ms / n_l * 1e-3
-            if bound == "tensor":
-                ach = work / avg_s / 1e12
-                peak = peaks["tflops_sustained"]
-                ent.update({"bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
-                            "frac": round(ach / peak, 4)})
-            else:
-                ach = work / avg_s / 1e9
-                peak = peaks["hbm_gbs"]
-                ent.update({"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                            "frac": round(ach / peak, 4)})
-        kernels.append(ent)
-    dom = next((k for k in kernels if "bound" in k), None)
-    roofline = None
-    if dom:
-        traffic = None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed ncu capture
-            per_img = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())["per_image_bytes"].get(dom["kernel"])
-            imgs_per_launch = B if dom["kernel"] in ("eigsh", "affinity", "rownorm") else args.vit_batch
-            traffic = per_img * imgs_per_launch if per_img else None
-        except Exception:
-            pass
-        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
-                    "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic, "share_of_step": dom["share"],
-                    "peak_source": peaks["source"] + (", sustained bf16 GEMM" if dom["bound"] == "tensor" else ""),
-                    "timing": "CUDA events around every launch of the class in a separate instrumented pass of the same steps"}
+    alg = {**vit_alg(P, d, depth - 1, N, B), **eig_alg(B, N, d, K, steps_mean)}
+    kernels = ctx.kernel_table(prof, alg)
+    traffic_db, traffic_file = load_traffic()
 
-    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (ViT); f32 (affinity, eigensolver)",
-            "data": "synthetic",
+    def traffic_lookup(kernel):
+        if not traffic_db:
+            return None
+        per_img = traffic_db.get("per_image_bytes", {}).get(kernel)
+        if not per_img:
+            return None
+        per_launch_images = B if kernel in ("eigsh", "affinity", "rownorm") else args.vit_batch
+        return per_img * per_launch_images
+    roofline = ctx.roofline(kernels, traffic_lookup)
+    if roofline is not None:
+        roofline["traffic_source"] = traffic_file
+
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": ctx.world, "steps": steps, "warmup": W,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (ViT); f32 (affinity, eigensolver)", "data": "synthetic",
             "config": {"workload": f"configs[1]: {S}x{S} {args.model} dense affinity K={K}", "images_per_step_per_gpu": B,
                        "vit_batch": args.vit_batch, "patches": N,
                        "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of uint8 images and {B * N * N * 4 / 1e6:.0f} MB of affinity matrices per step",
-                       "weights": "random init (upstream recipe), NCCL broadcast from rank 0" if world > 1 else "random init (upstream recipe)"},
+                       "weights": "random init (upstream recipe), NCCL broadcast from rank 0" if ctx.world > 1 else "random init (upstream recipe)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / steps,
+                    "what": "pinned host uint8 images in; K features [B,N,d] fp32 + eigenvalues + eigenvectors out to pinned "
+                            "host memory (the tensors of features/*.pth and eigs/*.pth); no file is written in the timed region"},
             "gpu_launches": int(launches),
             "eigensolver": {"converged": conv, "of": B, "lanczos_steps_mean": steps_mean},
             "roofline": roofline, "kernels": kernels}
 
-    # ---- CPU baseline + parity on a bounded sample (rank 0, N=1 only)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import eigs_ref
+    # ---- CPU baselines + parity on a bounded sample (rank 0, N=1 only)
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_cpu = args.cpu_sample if args.cpu_sample > 0 else 2 * max(1, min(cores // 2, 64))
-        ips, _, split = cpu_pool_images_per_sec(args.model, S, K, n_cpu, 1, 1)
-        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": f"{n_cpu} synthetic {S}x{S} images; fp32 eager DINO ViT + the reference's scipy eigsh route, "
-                                          f"{split['workers']} worker processes x {split['threads_per_worker']} BLAS threads",
-                                "split": split}
         n = min(args.parity_sample, B)
-        torch.set_num_threads(cores)
-        _, outs, _ = cpu_reference_images_per_sec(host_imgs[:n], args.model, K, sd, want_outputs=True)
-        feats = pipe._bufs["feats"][:n].cpu()
-        evecs = out[1][:n]
-        worst_same = worst_abs = worst_e2e = 0.0
+        feats = pipe._bufs["feats"][:n].cpu()          # features of the last step == images host_imgs[:n]
+        evecs = out[1][:n].numpy().copy()
+        tmp = tempfile.mkdtemp(prefix="dss_bench_")
+        paths = []
         for i in range(n):
-            ev_o, vec_o = eigs_ref.extract_eig(feats[i], K)  # oracle on OUR features: the 1e-4 criterion
-            v = evecs[i].numpy()
+            paths.append(os.path.join(tmp, f"f{i}.npy"))
+            np.save(paths[-1], feats[i].numpy())
+        n_cpu = args.cpu_sample if args.cpu_sample > 0 else max(n, 2 * max(1, min(cores // 2, 64)))
+        with CpuPool(args.model) as pool:
+            pool.map(_ref_worker_task, [(10_000 + i, S, K, False) for i in range(pool.workers)])          # warm-up
+            t0 = time.perf_counter()
+            # the CPU-baseline sample doubles as the end-to-end oracle of the parity images (seeds 0..n-1 = host_imgs[:n])
+            parts = pool.map(_ref_worker_task, [(i, S, K, i < n) for i in range(n_cpu)])
+            dt = time.perf_counter() - t0
+            same = pool.map(_eigs_worker_task, [(p_, K, {}) for p_ in paths])
+            split = {"workers": pool.workers, "threads_per_worker": pool.threads,
+                     "vit_s_per_image": sum(p_[0] for p_ in parts) / len(parts),
+                     "eigs_s_per_image": sum(p_[1] for p_ in parts) / len(parts)}
+        for p_ in paths:
+            os.unlink(p_)
+        os.rmdir(tmp)
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_cpu} synthetic {S}x{S} images; fp32 eager DINO ViT + the reference's scipy eigsh "
+                                          f"route, {split['workers']} worker processes x {split['threads_per_worker']} BLAS threads",
+                                "split": split,
+                                "eigs_only_images_per_s": split["workers"] / split["eigs_s_per_image"]}
+        if not args.no_as_shipped:
+            try:
+                line["cpu_baseline"]["as_shipped"] = as_shipped_baseline(args.model, S, K, 32, dev)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"]["as_shipped"] = {"error": repr(e)}
+
+        def errs(v, vo):
+            r, a = 0.0, 0.0
             for k in range(K):
-                vo = vec_o[k].numpy()
-                s = np.sign(np.dot(v[k], vo)) or 1.0
-                worst_same = max(worst_same, float(np.linalg.norm(v[k] - s * vo) / np.linalg.norm(vo)))
-                worst_abs = max(worst_abs, float(np.abs(v[k] - s * vo).max()))
-                ve = outs[i][2][k].numpy()                  # oracle end to end (fp32 ViT on the CPU)
-                s = np.sign(np.dot(v[k], ve)) or 1.0
-                worst_e2e = max(worst_e2e, float(np.linalg.norm(v[k] - s * ve) / np.linalg.norm(ve)))
-        line["parity"] = {"eigvec_max_abs_err": worst_abs, "eigvec_rel_l2_same_features": worst_same,
-                          "eigvec_rel_l2_end_to_end_vs_fp32_oracle": worst_e2e, "images": n, "tolerance": 1e-4}
-    if rank == 0:
+                sgn = np.sign(np.dot(v[k], vo[k])) or 1.0
+                r = max(r, float(np.linalg.norm(v[k] - sgn * vo[k]) / np.linalg.norm(vo[k])))
+                a = max(a, float(np.abs(v[k] - sgn * vo[k]).max()))
+            return r, a
+        rel_same = [errs(evecs[i], same[i][3]) for i in range(n)]
+        rel_e2e = [errs(evecs[i], parts[i][3])[0] for i in range(n)]
+        fb_same = [i for i in range(n) if same[i][1] == "SM-fallback"]
+        fb_e2e = [i for i in range(n) if parts[i][2] == "SM-fallback"]
+        line["parity"] = {
+            "images": n, "tolerance": 1e-4,
+            "eigvec_rel_l2_same_features": max(r for r, _ in rel_same),
+            "eigvec_max_abs_err": max(a for _, a in rel_same),
+            "eigvec_rel_l2_same_features_median": float(np.median([r for r, _ in rel_same])),
+            "images_over_tolerance_same_features": sum(1 for r, _ in rel_same if r > 1e-4),
+            "eigvec_rel_l2_end_to_end_vs_fp32_oracle": max(rel_e2e),
+            "eigvec_rel_l2_end_to_end_median": float(np.median(rel_e2e)),
+            "reference_singular_lu_fallback": {
+                "what": "images on which the reference's own float32 LU of D - W hit an exactly-zero pivot, the "
+                        "shift-invert eigsh raised and its except-branch (which='SM', extract.py:226-229) ran",
+                "same_features_images": len(fb_same),
+                "same_features_worst_rel_l2": max([rel_same[i][0] for i in fb_same], default=None),
+                "end_to_end_images": len(fb_e2e),
+                "end_to_end_worst_rel_l2": max([rel_e2e[i] for i in fb_e2e], default=None)}}
+    if ctx.rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _color_inputs(ctx, host_imgs, Hp, Wp):
+    """extract.py:199-204 on the synthetic images: PIL bilinear resize of the whole image to the patch grid."""
+    import numpy as np
+    from PIL import Image
+    lr = np.stack([np.array(Image.fromarray(im.numpy()).resize((Wp, Hp), Image.BILINEAR)) for im in host_imgs])
+    return lr
+
+
+def run_c3(ctx: Ctx):
+    """BASELINE configs[2]: dino_vitb8 on 480x480 (3600 patches), colour-KNN affinity (lambda 10), K=15."""
+    args, torch, dev = ctx.args, ctx.torch, ctx.dev
+    import numpy as np
+    model_name, S, K, lam = "dino_vitb8", 480, 15, 10.0
+    sd = ctx.weights(model_name)
+    B = args.images_per_step or 16
+    model = ctx.vit.DinoViT(model_name, sd, device=dev)
+    P, d, depth = model.patch_size, model.dim, model.depth
+    Hp = S // P
+    N = Hp * Hp
+    host_imgs = ctx.synth.blobs_batch(B, S, S, seed0=ctx.rank * B)
+    lr_u8 = _color_inputs(ctx, host_imgs, Hp, Hp)
+    host_rgb = torch.from_numpy((lr_u8 / 255.0).reshape(B, N, 3).astype(np.float32)).pin_memory()
+    host_imgs = host_imgs.pin_memory()
+    dev_imgs, dev_rgb = host_imgs.to(dev), host_rgb.to(dev)
+    feats = torch.empty(B, N, d, device=dev)
+    Wm = torch.empty(B, N, ctx.spectral.pitch(N), device=dev)
+    deg = torch.empty(B, N, device=dev)
+    last = {}
+
+    def step(imgs=dev_imgs, rgb=dev_rgb):
+        model.forward_k(imgs, out=feats)
+        cc = ctx.spectral.knn_color_counts(rgb, Hp, Hp)
+        ctx.spectral.affinity(feats, True, True, cc, lam, out=Wm, degree=deg)
+        last["out"] = ctx.spectral.eigsh_laplacian(Wm, N, K, degree=deg)
+    W, steps = max(args.warmup, 3), args.steps
+    ctx.sampler.start()
+    ms, launches = ctx.timed(step, steps, W)
+    value = ctx.world * B * steps / (ms * 1e-3)
+    info = last["out"][2]
+    steps_mean = float(info[:, 0].float().mean().item())
+
+    def step_e2e():
+        step(host_imgs.to(dev, non_blocking=True), host_rgb.to(dev, non_blocking=True))
+        o = last["out"]
+        last["host"] = (o[0].cpu(), o[1].cpu(), feats.cpu())
+    ms_e2e, _ = ctx.timed(step_e2e, steps, 1)
+    clocks = ctx.sampler.stop()
+    ctx._prof_steps = steps
+    prof = ctx.profile(step, steps)
+    alg = {**vit_alg(P, d, depth - 1, N, B), **eig_alg(B, N, d, K, steps_mean)}
+    kernels = ctx.kernel_table(prof, alg)
+    line = {"metric": "images/sec (features+eigs, 480px dino_vitb8 colour-KNN K=15)", "value": value, "unit": "images/s",
+            "n_gpus": ctx.world, "steps": steps, "warmup": W, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (ViT); f32 (affinity, eigensolver)",
+            "data": "synthetic",
+            "config": {"workload": "configs[2]: 480x480 dino_vitb8 (3600 patches), colour-KNN affinity lambda=10, K=15",
+                       "images_per_step_per_gpu": B, "patches": N,
+                       "l2": f"inputs larger than L2: {B * N * N * 4 / 1e6:.0f} MB of affinity matrices per step"},
+            "clocks": clocks,
+            "e2e": {"value": ctx.world * B * steps / (ms_e2e * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(host_imgs.numel() + host_rgb.numel() * 4),
+                    "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in last["host"])),
+                    "what": "pinned host images + low-res colour images in; features, eigenvalues, eigenvectors out (synchronous copies)"},
+            "gpu_launches": int(launches),
+            "eigensolver": {"converged": int(info[:, 1].sum().item()), "of": B, "lanczos_steps_mean": steps_mean},
+            "roofline": ctx.roofline(kernels), "kernels": kernels}
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = min(8, B)
+        tmp = tempfile.mkdtemp(prefix="dss_bench_")
+        fh = feats[:n].cpu()
+        jobs = []
+        for i in range(n):
+            np.save(os.path.join(tmp, f"f{i}.npy"), fh[i].numpy())
+            jobs.append((os.path.join(tmp, f"f{i}.npy"), K, {"image_lr": lr_u8[i] / 255.0, "image_color_lambda": lam}))
+        with CpuPool(model_name, threads_per_worker=max(1, cores // n), max_workers=n, need_vit=False) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_eigs_worker_task, jobs)
+            dt = time.perf_counter() - t0
+            wk, th = pool.workers, pool.threads
+        ev_h = last["out"][1][:n].cpu().numpy()
+        worst = 0.0
+        for i in range(n):
+            for k in range(K):
+                vo = res[i][3][k]
+                sgn = np.sign(np.dot(ev_h[i][k], vo)) or 1.0
+                worst = max(worst, float(np.linalg.norm(ev_h[i][k] - sgn * vo) / np.linalg.norm(vo)))
+        line["cpu_baseline"] = {"value": n / dt, "unit": "images/s (eigs stage only)", "cores": cores, "kind": "port",
+                                "sample": f"{n} images: the reference's extract_eigs arithmetic (colour-KNN incl. exact KNN, degree, "
+                                          f"scipy eigsh) on the GPU path's own features, {wk} workers x {th} BLAS threads; the "
+                                          "fp32 ViT-B/8 on the CPU is not timed (about 1 TFLOP per image)",
+                                "per_image_s": sum(r[0] for r in res) / n,
+                                "sm_fallback_images": sum(1 for r in res if r[1] == "SM-fallback")}
+        line["parity"] = {"images": n, "eigvec_rel_l2_same_features_worst": worst,
+                          "note": "K=15 at N=3600 has eigen-gaps down to 1e-3: the reference's own float32 jitter (1e-7 / gap) "
+                                  "is part of this number; tests/test_configs_gpu.py applies the gap-aware tolerance"}
+        for j in jobs:
+            os.unlink(j[0])
+        os.rmdir(tmp)
+    if ctx.rank == 0:
+        print(json.dumps(line))
+
+
+def run_c4(ctx: Ctx):
+    """BASELINE configs[3]: VOC-shaped image sizes (synth.VOC_SHAPES table, seeded), dino_vits16, K=5; the global list
+    is sharded rank-strided, every rank processes `images_per_step` images per step grouped by shape."""
+    args, torch, dev = ctx.args, ctx.torch, ctx.dev
+    import numpy as np
+    from collections import Counter
+    model_name, K = "dino_vits16", 5
+    sd = ctx.weights(model_name)
+    B = args.images_per_step or 592
+    model = ctx.vit.DinoViT(model_name, sd, device=dev)
+    P, d, depth = model.patch_size, model.dim, model.depth
+    total = 50_000
+    shapes = ctx.synth.voc_shapes(total, seed=0)                       # the global list (SURVEY 8d), sorted order = index
+    mine = ctx.pipeline.shard_indices(total, ctx.rank, ctx.world)[:B]  # this rank's first step of its shard
+    groups = Counter(shapes[i] for i in mine)
+    pipes, host, devi = {}, {}, {}
+    for (H, Wd), cnt in sorted(groups.items()):
+        base = ctx.synth.blobs_batch(min(cnt, 24), H, Wd, seed0=1000 * H + Wd + ctx.rank)   # 24 distinct images per shape, tiled
+        reps = (cnt + base.shape[0] - 1) // base.shape[0]
+        host[(H, Wd)] = base.repeat(reps, 1, 1, 1)[:cnt].contiguous().pin_memory()
+        devi[(H, Wd)] = host[(H, Wd)].to(dev)
+        pipes[(H, Wd)] = ctx.pipeline.SpectralPipeline(model_name, K=K, device=dev, vit_batch=128, model=model)
+    infos = {}
+
+    def step():
+        for key, p_ in pipes.items():
+            infos[key] = p_.run_device(devi[key])[2]
+
+    def step_e2e():
+        for key, p_ in pipes.items():
+            infos[key] = p_.run_host(host[key])[2]
+    W, steps = max(args.warmup, 3), args.steps
+    ctx.sampler.start()
+    ms, launches = ctx.timed(step, steps, W)
+    ms_e2e, _ = ctx.timed(step_e2e, steps, 1)
+    clocks = ctx.sampler.stop()
+    ctx._prof_steps = steps
+    prof = ctx.profile(step, steps)
+    alg = {}
+    for (H, Wd), cnt in groups.items():
+        N = (H // P) * (Wd // P)
+        m_steps = float(infos[(H, Wd)][:, 0].float().mean().item())
+        for k_, (bound, work) in {**vit_alg(P, d, depth - 1, N, cnt), **eig_alg(cnt, N, d, K, m_steps)}.items():
+            alg[k_] = (bound, alg.get(k_, (bound, 0.0))[1] + work)
+    kernels = ctx.kernel_table(prof, alg)
+    conv = sum(int(v[:, 1].sum().item()) for v in infos.values())
+    line = {"metric": "images/sec (features+eigs, VOC-shaped sizes, dino_vits16 K=5)", "value": ctx.world * B * steps / (ms * 1e-3),
+            "unit": "images/s", "n_gpus": ctx.world, "steps": steps, "warmup": W, "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (ViT); f32 (affinity, eigensolver)", "data": "synthetic",
+            "config": {"workload": "configs[3]: 50k-image VOC-shaped list (seeded size table), rank-strided shards, dino_vits16, K=5",
+                       "images_per_step_per_gpu": B, "shape_groups": {f"{h}x{w}": c for (h, w), c in sorted(groups.items())},
+                       "size_table": [[list(s_), w_] for s_, w_ in ctx.synth.VOC_SHAPES],
+                       "l2": "inputs larger than L2 (hundreds of MB of images and affinity matrices per step)"},
+            "clocks": clocks,
+            "e2e": {"value": ctx.world * B * steps / (ms_e2e * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(sum(h.numel() for h in host.values())),
+                    "d2h_bytes_per_step": int(sum(c * (K + K * (hh // P) * (ww // P) + 4) * 4 for (hh, ww), c in groups.items())),
+                    "what": "per shape group: pinned host images in, eigenvalues + eigenvectors out (run_host)"},
+            "gpu_launches": int(launches), "eigensolver": {"converged": conv, "of": B},
+            "roofline": ctx.roofline(kernels), "kernels": kernels}
+    if ctx.rank == 0:
+        print(json.dumps(line))
+
+
+def run_c5(ctx: Ctx):
+    """BASELINE configs[4]: dino_vitb8 on 640x640 (6400 patches), K=32, plus the N sweep {900, 1600, 3600, 6400} of the
+    affinity + eigensolver stage with the reference's CPU extract_eigs arithmetic timed beside it."""
+    args, torch, dev = ctx.args, ctx.torch, ctx.dev
+    import numpy as np
+    model_name, K = "dino_vitb8", 32
+    sd = ctx.weights(model_name)
+    B = args.images_per_step or 4
+    model = ctx.vit.DinoViT(model_name, sd, device=dev)
+    P, d, depth = model.patch_size, model.dim, model.depth
+    W, steps = max(args.warmup, 3), args.steps
+    ctx.sampler.start()
+    sweep = []
+    main = None
+    for S in (240, 320, 480, 640):
+        Hp = S // P
+        N = Hp * Hp
+        nb = B if S == 640 else max(B, min(64, 23040 // max(1, N // 100)))    # more images at small N (fills the GPU)
+        host_imgs = ctx.synth.blobs_batch(min(nb, 8), S, S, seed0=7 + ctx.rank)
+        host_imgs = host_imgs.repeat((nb + 7) // 8, 1, 1, 1)[:nb].contiguous().pin_memory()
+        dev_imgs = host_imgs.to(dev)
+        feats = torch.empty(nb, N, d, device=dev)
+        Wm = torch.empty(nb, N, ctx.spectral.pitch(N), device=dev)
+        deg = torch.empty(nb, N, device=dev)
+        last = {}
+
+        def step():
+            vb = 8 if S >= 480 else 32
+            for s_ in range(0, nb, vb):
+                model.forward_k(dev_imgs[s_:s_ + vb], out=feats[s_:s_ + vb])
+            ctx.spectral.affinity(feats, out=Wm, degree=deg)
+            last["out"] = ctx.spectral.eigsh_laplacian(Wm, N, K, degree=deg)
+        ms, launches = ctx.timed(step, steps, W)
+        info = last["out"][2]
+        m_steps = float(info[:, 0].float().mean().item())
+        ctx._prof_steps = steps
+        prof = ctx.profile(step, steps)
+        alg = {**vit_alg(P, d, depth - 1, N, nb), **eig_alg(nb, N, d, K, m_steps)}
+        kernels = ctx.kernel_table(prof, alg)
+        row = {"image_size": S, "patches": N, "images_per_step": nb, "images_per_s": ctx.world * nb * steps / (ms * 1e-3),
+               "ms_per_step": ms / steps, "lanczos_steps_mean": m_steps, "converged": int(info[:, 1].sum().item()),
+               "kernels": [k_ for k_ in kernels if k_["kernel"] in ("eigsh", "affinity", "attention", "gemm_fc1", "gemm_qkv")]}
+        if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = 2 if N >= 3600 else 4
+            tmp = tempfile.mkdtemp(prefix="dss_bench_")
+            fh = feats[:n].cpu()
+            jobs = []
+            for i in range(n):
+                np.save(os.path.join(tmp, f"f{i}.npy"), fh[i].numpy())
+                jobs.append((os.path.join(tmp, f"f{i}.npy"), K, {}))
+            with CpuPool(model_name, threads_per_worker=max(1, cores // n), max_workers=n, need_vit=False) as pool:
+                t0 = time.perf_counter()
+                res = pool.map(_eigs_worker_task, jobs)
+                dt = time.perf_counter() - t0
+            for j in jobs:
+                os.unlink(j[0])
+            os.rmdir(tmp)
+            ev_h = last["out"][1][:n].cpu().numpy()
+            lam_h = last["out"][0][:n].cpu().numpy()
+            row["cpu_extract_eigs"] = {"images_per_s": n / dt, "per_image_s": sum(r[0] for r in res) / n, "images": n,
+                                       "cores": cores, "sm_fallback_images": sum(1 for r in res if r[1] == "SM-fallback"),
+                                       "eigenvalue_max_abs_diff": float(max(np.abs(lam_h[i] - res[i][2]).max() for i in range(n)))}
+        sweep.append(row)
+        if S == 640:
+            main = (row, kernels, launches, nb, N, info)
+        del feats, Wm, deg, dev_imgs
+        torch.cuda.empty_cache()
+    clocks = ctx.sampler.stop()
+    row, kernels, launches, nb, N, info = main
+    line = {"metric": "images/sec (features+eigs, 640px dino_vitb8 K=32)", "value": row["images_per_s"], "unit": "images/s",
+            "n_gpus": ctx.world, "steps": steps, "warmup": W, "ms_per_step": row["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (ViT); f32 (affinity, eigensolver)",
+            "data": "synthetic",
+            "config": {"workload": "configs[4]: 640x640 dino_vitb8 (6400 patches), dense affinity, K=32; sweep over N",
+                       "images_per_step_per_gpu": nb, "patches": N,
+                       "l2": f"inputs larger than L2: {nb * N * N * 4 / 1e6:.0f} MB of affinity matrices per step"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "eigensolver": {"converged": int(info[:, 1].sum().item()), "of": nb, "lanczos_steps_mean": row["lanczos_steps_mean"]},
+            "roofline": ctx.roofline(kernels), "kernels": kernels, "sweep": sweep}
+    if ctx.rank == 0:
+        print(json.dumps(line))
 
 
 def main():
@@ -435,8 +883,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
-    else:
-        run_ours(args, rank, local_rank, world)
+        return
+    ctx = Ctx(args, rank, local_rank, world)
+    {"c2": run_c2, "c3": run_c3, "c4": run_c4, "c5": run_c5}[args.workload](ctx)
+    ctx.finish()
 
 
 if __name__ == "__main__":

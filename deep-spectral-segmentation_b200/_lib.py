@@ -29,7 +29,7 @@ class VitBlockWeights(C.Structure):
 
 class VitWeights(C.Structure):
     _fields_ = [("patch_w", c_void_p), ("patch_b", c_void_p), ("cls_token", c_void_p), ("pos_embed", c_void_p),
-                ("blocks", C.POINTER(VitBlockWeights))]
+                ("blocks", C.POINTER(VitBlockWeights)), ("norm_w", c_void_p), ("norm_b", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/dss_b200.h
@@ -48,6 +48,7 @@ PROTOTYPES = {
                                   c_void_p]),
     "dss_vit_forward_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                        c_void_p]),
+    "dss_vit_forward_cls": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dss_vit_pos_embed": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "dss_pos_embed_interp_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dss_op_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
@@ -69,6 +70,12 @@ PROTOTYPES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dss_eigsh_topk": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dss_rw_affinity_add": (c_int, [c_void_p, c_int, c_int, c_int, c_float, C.c_double, c_void_p, c_int, c_void_p,
+                                    c_void_p]),
+    "dss_segment_threshold": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dss_segment_kmeans": (c_int, [c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, c_int, c_int, c_int, c_void_p,
+                                   c_int, c_int, c_int, c_int, C.c_uint, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
     "dss_upsample_bilinear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dss_normalize_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }

@@ -116,3 +116,67 @@ extern "C" int dss_knn_color_counts(const float* rgb, int B, int Hl, int Wl, uin
   }
   return DSS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Random-walk colour affinity (reference extract/extract_utils.py:191-204 -> pymatting.laplacian.rw_laplacian.
+// _rw_laplacian(image, sigma, radius=1)): for every pixel i and every offset (dy, dx) in [-1, 1]^2 the CLAMPED
+// neighbour j gets the weight exp(-coef * ||z_i - z_j||^2) (float64, z = rgb / 255); csr_matrix sums duplicates, which
+// border clamping produces (a corner pixel lists itself four times). The reference then densifies to float32, scales by
+// image_color_lambda and adds it to the feature affinity (extract.py:216,221). The matrix has <= 9 entries per row,
+// so this kernel adds them in place to the dense W the affinity GEMM wrote -- one thread per pixel owns row i (its
+// duplicates are merged in float64 first, exactly like the csr constructor) -- and adds the row's total to `degree`.
+namespace dss {
+
+__global__ void __launch_bounds__(128)
+rw_affinity_add_kernel(const uint8_t* __restrict__ rgb, int Hl, int Wl, float lambda, double coef, float* __restrict__ W,
+                       int ldw, float* __restrict__ degree) {
+  const int N = Hl * Wl;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= N) return;
+  const uint8_t* img = rgb + (size_t)b * N * 3;
+  const int y = i / Wl, x = i % Wl;
+  const double zi[3] = {img[i * 3] / 255.0, img[i * 3 + 1] / 255.0, img[i * 3 + 2] / 255.0};
+  int js[9];
+  double ws[9];
+  int cnt = 0;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x2 = max(0, min(Wl - 1, x + dx)), y2 = max(0, min(Hl - 1, y + dy));
+      const int j = x2 + y2 * Wl;
+      double d2 = 0.0;
+      for (int c = 0; c < 3; ++c) {
+        const double diff = zi[c] - img[j * 3 + c] / 255.0;
+        d2 += diff * diff;
+      }
+      const double nrm = sqrt(d2);                 // np.linalg.norm(zi - zj) ** 2
+      const double w = exp(-coef * (nrm * nrm));
+      int k = 0;
+      for (; k < cnt; ++k)
+        if (js[k] == j) break;
+      if (k < cnt) ws[k] += w;                     // duplicate (i, j): summed, as scipy's csr constructor does
+      else { js[cnt] = j; ws[cnt] = w; ++cnt; }
+    }
+  float* row = W + ((size_t)b * N + i) * ldw;
+  float dsum = 0.f;
+  for (int k = 0; k < cnt; ++k) {
+    const float add = static_cast<float>(ws[k]) * lambda;   // W_color.astype(float32) * image_color_lambda
+    row[js[k]] += add;                                       // W_feat + ...
+    dsum += add;
+  }
+  if (degree) degree[(size_t)b * N + i] += dsum;
+}
+
+}  // namespace dss
+
+extern "C" int dss_rw_affinity_add(const uint8_t* rgb_u8, int B, int Hl, int Wl, float color_lambda, double coef,
+                                   float* Wmat, int ldw, float* degree, dss_stream_t stream) {
+  DSS_REQUIRE(rgb_u8 && Wmat, "rw_affinity: null pointer");
+  DSS_REQUIRE(B > 0 && Hl > 0 && Wl > 0, "rw_affinity: empty problem");
+  DSS_REQUIRE(ldw >= Hl * Wl, "rw_affinity: ldw < N");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LaunchScope scope(st, KC_KNN);
+  rw_affinity_add_kernel<<<dim3(cdiv(Hl * Wl, 128), B), 128, 0, st>>>(rgb_u8, Hl, Wl, color_lambda, coef, Wmat, ldw, degree);
+  DSS_CHECK_CUDA(cudaGetLastError());
+  return DSS_OK;
+}

@@ -28,6 +28,22 @@ int launch_cls_row(float* x, const float* cls, const float* pos, int B, int T, i
 int launch_layernorm(const float* x, const float* g, const float* b, void* y, int M, int d, float eps, cudaStream_t st);
 int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cudaStream_t st);
 
+// y[b, :] = LayerNorm(x[b * row_stride, :]) * gamma + beta in fp32 (one warp per row): the final norm of the CLS token
+__global__ void __launch_bounds__(128)
+layernorm_rows_f32_kernel(const float* __restrict__ x, long long row_stride, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float* __restrict__ y, int rows, int d, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * row_stride;
+  float s = 0.f;
+  for (int i = lane; i < d; i += 32) s += xr[i];
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+  for (int i = lane; i < d; i += 32) { const float a = xr[i] - mean; q = fmaf(a, a, q); }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+  for (int i = lane; i < d; i += 32) y[(long long)row * d + i] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
+}
+
 __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2half_rn(src[i]);
@@ -48,6 +64,7 @@ struct dss_vit {
   size_t arena_bytes = 0;
   __half* patch_w = nullptr;
   float *patch_b = nullptr, *cls = nullptr;
+  float *norm_w = nullptr, *norm_b = nullptr;   // final LayerNorm (only needed by dss_vit_forward_cls)
   CUtensorMap tm_patch;
   std::vector<dss::BlockW> blocks;
   std::vector<float> pos_host;                        // [1 + grid0^2, d] fp32 host copy
@@ -158,8 +175,10 @@ static VitWs carve(const dss_vit_config& c, int B, int H, int W, void* base) {
   return w;
 }
 
-static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_full, bool k_proj, float* out, void* ws,
+// mode 0: K projection of block n_full (features), 1: residual stream [B, T, d], 2: final-norm CLS token [B, d]
+static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_full, int mode, float* out, void* ws,
                    size_t ws_bytes, cudaStream_t st) {
+  const bool k_proj = mode == 0;
   DSS_REQUIRE(h && h->loaded, "vit: weights not loaded");
   DSS_REQUIRE(img && out && ws, "vit: null pointer");
   const dss_vit_config& c = h->cfg;
@@ -221,6 +240,12 @@ static int vit_run(dss_vit* h, const uint8_t* img, int B, int H, int W, int n_fu
     if ((rc = gemm_f16_tc(tm_xn, bw.tm_k, nullptr, bw.qkv_b + d, out, M, d, d, DSS_EPI_DROPCLS_F32, nullptr, T, Np, st,
                           KC_GEMM_KPROJ, 128)))
       return rc;
+  } else if (mode == 2) {
+    // upstream VisionTransformer.forward: x = norm(x); return x[:, 0]  (LayerNorm is row-wise: only the CLS rows)
+    DSS_REQUIRE(h->norm_w && h->norm_b, "vit: the final LayerNorm weights (norm.weight / norm.bias) were not loaded");
+    LaunchScope scope(st, KC_LAYERNORM);
+    layernorm_rows_f32_kernel<<<cdiv(B, 4), 128, 0, st>>>(w.x, (long long)T * d, h->norm_w, h->norm_b, out, B, d, c.ln_eps);
+    DSS_CHECK_CUDA(cudaGetLastError());
   } else {
     DSS_CHECK_CUDA(cudaMemcpyAsync(out, w.x, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
@@ -264,6 +289,7 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
     return o;
   };
   const size_t o_patch_w = reserve(d * Kp * 2), o_patch_b = reserve(d * 4), o_cls = reserve(d * 4);
+  const size_t o_norm_w = reserve(d * 4), o_norm_b = reserve(d * 4);
   struct Off { size_t qkv_w, proj_w, fc1_w, fc2_w, ln1_w, ln1_b, ln2_w, ln2_b, qkv_b, proj_b, fc1_b, fc2_b; };
   std::vector<Off> bo(c.depth);
   for (int l = 0; l < c.depth; ++l) {
@@ -297,6 +323,13 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
   h->patch_w = reinterpret_cast<__half*>(base + o_patch_w);
   h->patch_b = reinterpret_cast<float*>(base + o_patch_b);
   h->cls = reinterpret_cast<float*>(base + o_cls);
+  h->norm_w = h->norm_b = nullptr;
+  if (w->norm_w && w->norm_b) {
+    if ((rc = cpy(w->norm_w, o_norm_w, d))) return rc;
+    if ((rc = cpy(w->norm_b, o_norm_b, d))) return rc;
+    h->norm_w = reinterpret_cast<float*>(base + o_norm_w);
+    h->norm_b = reinterpret_cast<float*>(base + o_norm_b);
+  }
   if ((rc = make_tmap_f16(&h->tm_patch, h->patch_w, (int)d, (int)Kp, 128 / 2))) return rc;
   h->blocks.resize(c.depth);
   for (int l = 0; l < c.depth; ++l) {
@@ -351,14 +384,20 @@ extern "C" int dss_vit_forward_k(dss_vit_t* h, const uint8_t* images_u8, int B, 
   const int depth = h->cfg.depth;
   DSS_REQUIRE(which_block >= -depth && which_block < depth, "vit_forward_k: which_block %d out of range", which_block);
   const int blk = which_block < 0 ? which_block + depth : which_block;
-  return vit_run(h, images_u8, B, H, W, blk, true, k_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  return vit_run(h, images_u8, B, H, W, blk, 0, k_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dss_vit_forward_tokens(dss_vit_t* h, const uint8_t* images_u8, int B, int H, int W, int n_blocks,
                                       float* x_out, void* ws, size_t ws_bytes, dss_stream_t stream) {
   DSS_REQUIRE(h, "vit_forward_tokens: null handle");
   DSS_REQUIRE(n_blocks >= 0 && n_blocks <= h->cfg.depth, "vit_forward_tokens: n_blocks %d out of range", n_blocks);
-  return vit_run(h, images_u8, B, H, W, n_blocks, false, x_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  return vit_run(h, images_u8, B, H, W, n_blocks, 1, x_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dss_vit_forward_cls(dss_vit_t* h, const uint8_t* images_u8, int B, int H, int W, float* cls_out, void* ws,
+                                   size_t ws_bytes, dss_stream_t stream) {
+  DSS_REQUIRE(h, "vit_forward_cls: null handle");
+  return vit_run(h, images_u8, B, H, W, h->cfg.depth, 2, cls_out, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dss_vit_pos_embed(dss_vit_t* h, int Hp, int Wp, float* out, dss_stream_t stream) {

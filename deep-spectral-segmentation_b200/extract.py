@@ -3,19 +3,22 @@
     extract_features  (:21-116)   images -> features/{id}.pth      {'k','indices','file','id','model_name','patch_size','shape'}
     _extract_eig      (:119-244)  one features file -> eigs/{image_id}.pth  {'eigenvalues','eigenvectors'}
     extract_eigs      (:247-280)  directory of features files -> eigs files (batched on the GPU)
-    extract_all                   fused: images -> both file layouts without the disk round-trip (new)
+    extract_all                   fused: images -> both file layouts (+ optional segmentations) without the disk round-trip
+    extract_single_region_segmentations / extract_multi_region_segmentations  (:283-411)  eigs -> PNG masks (GPU kernels)
+    extract_bbox_features (:500-544)  DINO CLS embedding of every bounding-box crop
 
-Same argument names, defaults, file layouts and skip-if-exists behaviour; all arithmetic runs in libdss_b200."""
+Same argument names, defaults, file layouts and skip-if-exists behaviour; all arithmetic runs in libdss_b200. Host I/O
+(decode, pinned staging, .pth / PNG writers) is threaded, see io_pipeline.py."""
 from __future__ import annotations
 
 from collections import defaultdict
 from pathlib import Path
-from typing import List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
 
-from . import _lib, spectral
+from . import _lib, io_pipeline, segment, spectral
 from . import extract_utils as utils
 
 torch.set_grad_enabled(False)  # extract.py:838
@@ -33,9 +36,41 @@ def _feature_dict(k: torch.Tensor, index: int, file: str, model_name: str, patch
             "patch_size": patch_size, "shape": (1, 3, H, W)}
 
 
+class _Batcher:
+    """Groups items by a shape key. A group is handed to ``flush`` when it reaches ``batch_size``; when more than
+    ``max_pending`` items are waiting in total (data sets with hundreds of distinct image sizes, e.g. VOC), the
+    largest group is flushed early, so host memory stays bounded and outputs appear steadily."""
+
+    def __init__(self, batch_size: int, flush, max_pending: Optional[int] = None):
+        self.batch_size = max(1, int(batch_size))
+        self.flush_fn = flush
+        self.max_pending = max_pending if max_pending is not None else 8 * self.batch_size
+        self.groups: Dict[object, list] = defaultdict(list)
+        self.count = 0
+
+    def _flush(self, key):
+        items = self.groups.pop(key, [])
+        self.count -= len(items)
+        if items:
+            self.flush_fn(key, items)
+
+    def add(self, key, item):
+        self.groups[key].append(item)
+        self.count += 1
+        if len(self.groups[key]) >= self.batch_size:
+            self._flush(key)
+        elif self.count > self.max_pending:
+            self._flush(max(self.groups, key=lambda k: len(self.groups[k])))
+
+    def finish(self):
+        for key in list(self.groups.keys()):
+            self._flush(key)
+
+
 def extract_features(images_list: str, images_root: Optional[str], model_name: str, batch_size: int, output_dir: str,
                      which_block: int = -1, checkpoint: Optional[str] = None, seed: Optional[int] = None,
-                     random_init: bool = False, yes: Optional[bool] = None):
+                     random_init: bool = False, yes: Optional[bool] = None, num_workers: Optional[int] = None,
+                     num_workers_out: int = 8):
     """
     Extract features from a list of images.
 
@@ -57,42 +92,44 @@ def extract_features(images_list: str, images_root: Optional[str], model_name: s
     filenames = Path(images_list).read_text().splitlines()
     dataset = utils.ImagesDataset(filenames=filenames, images_root=images_root)
     print(f"Dataset size: {len(dataset)=}")
+    rings: Dict[tuple, io_pipeline.PinnedRing] = {}
 
-    pending: dict = defaultdict(list)  # (H, W) -> [(image, file, index)]
+    with io_pipeline.AsyncWriter(num_workers_out) as writer:
+        def flush(shape_key, items):
+            H, W = shape_key
+            ring = rings.get(shape_key)
+            if ring is None:
+                ring = rings[shape_key] = io_pipeline.PinnedRing(shape_key, max(1, int(batch_size)), dev)
+            slot, host = ring.stage([it[0] for it in items])
+            k = model.forward_k(ring.to_device(slot, host), which_block=which_block).cpu()
+            for j, (_, file, index) in enumerate(items):
+                out = _feature_dict(k[j:j + 1].clone(), index, file, model_name, patch_size, H, W)
+                writer.submit(out, Path(output_dir) / f"{out['id']}.pth")
 
-    def flush(shape_key):
-        items = pending.pop(shape_key, [])
-        if not items:
-            return
-        H, W = shape_key
-        batch = torch.stack([it[0] for it in items]).pin_memory().to(dev, non_blocking=True)
-        k = model.forward_k(batch, which_block=which_block).cpu()
-        for j, (_, file, index) in enumerate(items):
-            out = _feature_dict(k[j:j + 1].clone(), index, file, model_name, patch_size, H, W)
-            torch.save(out, str(Path(output_dir) / f"{out['id']}.pth"))
-
-    for i in range(len(dataset)):
-        file = dataset.filenames[i]
-        output_file = Path(output_dir) / f"{Path(file).stem}.pth"
-        if output_file.is_file():
-            print(f"Skipping existing file {str(output_file)}")
-            continue
-        image, file, index = dataset[i]
-        key = (int(image.shape[0]), int(image.shape[1]))
-        pending[key].append((image, file, index))
-        if len(pending[key]) >= max(1, int(batch_size)):
-            flush(key)
-    for key in list(pending.keys()):
-        flush(key)
+        batcher = _Batcher(batch_size, flush)
+        todo = []
+        for i in range(len(dataset)):
+            output_file = Path(output_dir) / f"{Path(dataset.filenames[i]).stem}.pth"
+            if output_file.is_file():
+                print(f"Skipping existing file {str(output_file)}")
+            else:
+                todo.append(i)
+        for image, file, index in io_pipeline.ImagePrefetcher(dataset.__getitem__, todo, num_workers):
+            batcher.add((int(image.shape[0]), int(image.shape[1])), (image, file, index))
+        batcher.finish()
     print(f"Saved features to {output_dir}")
 
 
-def _load_image_lr(images_root: str, image_id: str, W_lr: int, H_lr: int) -> np.ndarray:
-    """extract.py:199-204: PIL open, BILINEAR resize of the whole image to (W_lr, H_lr), /255 -> (H_lr, W_lr, 3)."""
+def _load_image_lr_u8(images_root: str, image_id: str, W_lr: int, H_lr: int) -> np.ndarray:
+    """extract.py:199-203: PIL open (no .convert), BILINEAR resize of the WHOLE image to (W_lr, H_lr) -> uint8 pixels."""
     from PIL import Image
     image_file = str(Path(images_root) / f"{image_id}.jpg")
-    image_lr = Image.open(image_file).resize((W_lr, H_lr), Image.BILINEAR)
-    return np.array(image_lr) / 255.0
+    return np.array(Image.open(image_file).resize((W_lr, H_lr), Image.BILINEAR))
+
+
+def _load_image_lr(images_root: str, image_id: str, W_lr: int, H_lr: int) -> np.ndarray:
+    """extract.py:199-204: the low-resolution image / 255 -> float64 (H_lr, W_lr, 3)."""
+    return _load_image_lr_u8(images_root, image_id, W_lr, H_lr) / 255.0
 
 
 def _check_supported(which_matrix, which_color_matrix, image_color_lambda):
@@ -100,19 +137,50 @@ def _check_supported(which_matrix, which_color_matrix, image_color_lambda):
         raise RuntimeError("which_matrix='affinity_torch' calls torch.eig, which PyTorch removed (dead in the reference)")
     if which_matrix not in ("laplacian", "matting_laplacian", "affinity", "affinity_svd"):
         raise ValueError(f"unknown which_matrix={which_matrix!r}")
-    if which_matrix in ("laplacian", "matting_laplacian") and image_color_lambda > 0 and which_color_matrix != "knn":
-        # 'rw' needs pymatting's _rw_laplacian, a third-party routine that is neither installed nor restatable offline
-        raise NotImplementedError(f"which_color_matrix={which_color_matrix!r}: only 'knn' is built")
+    if which_matrix in ("laplacian", "matting_laplacian") and image_color_lambda > 0 \
+            and which_color_matrix not in ("knn", "rw"):
+        raise ValueError(f"unknown which_color_matrix={which_color_matrix!r} (the reference knows 'knn' and 'rw')")
+
+
+def _color_inputs(images_root, image_ids, W_lr, H_lr, which_color_matrix, dev):
+    """Low-resolution colour images of a batch on the device: fp32 /255 for 'knn', the uint8 pixels for 'rw'."""
+    lr = np.stack([_load_image_lr_u8(images_root, i, W_lr, H_lr) for i in image_ids]).reshape(len(image_ids), H_lr * W_lr, 3)
+    if which_color_matrix == "rw":
+        return torch.from_numpy(np.ascontiguousarray(lr)).to(dev)
+    return torch.from_numpy((lr / 255.0).astype(np.float32)).to(dev)
+
+
+def _solve_with_retry(solve, n_images: int, N: int):
+    """Runs ``solve(sel, max_steps)`` (sel = None for the whole batch, else a list of batch rows) and retries the images
+    whose Lanczos run did not reach its tolerance or came back non-finite with the largest possible Krylov space
+    (max_steps = N - 1). The reference's own safety net is a second eigsh call (which='SM', extract.py:226-234).
+    Returns (eigenvalues, eigenvectors, info, failed rows) on the CPU."""
+    evals, evecs, info = (t.cpu() for t in solve(None, 0))
+    bad = [i for i in range(n_images)
+           if int(info[i, 1]) == 0 or not bool(torch.isfinite(evecs[i]).all() and torch.isfinite(evals[i]).all())]
+    failed = []
+    if bad:
+        ev2, vec2, info2 = (t.cpu() for t in solve(bad, max(N - 1, 1)))
+        for j, i in enumerate(bad):
+            ok = int(info2[j, 1]) == 1 and bool(torch.isfinite(vec2[j]).all() and torch.isfinite(ev2[j]).all())
+            if ok:
+                evals[i], evecs[i], info[i] = ev2[j], vec2[j], info2[j]
+            else:
+                failed.append(i)
+    return evals, evecs, info, failed
 
 
 def _eigs_for_group(data_dicts: List[dict], K: int, images_root, which_features, normalize, lapnorm, threshold_at_zero,
-                    image_downsample_factor, image_color_lambda, dev, which_matrix="laplacian"
-                    ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """One GPU batch: feature dicts whose patch grids have the same size -> (eigenvalues [B,K], eigenvectors [B,K,N]) CPU."""
+                    image_downsample_factor, image_color_lambda, dev, which_matrix="laplacian", which_color_matrix="knn"
+                    ) -> Tuple[torch.Tensor, torch.Tensor, List[int]]:
+    """One GPU batch: feature dicts whose patch grids have the same size -> (eigenvalues [B,K], eigenvectors [B,K,N],
+    rows whose solve failed even after the retry) on the CPU."""
     feats = torch.stack([d[which_features].squeeze() for d in data_dicts]).to(torch.float32)
     feats = feats.pin_memory().to(dev, non_blocking=True)
     if which_matrix in ("affinity", "affinity_svd"):
-        evals, evecs, info = spectral.affinity_eigs(feats, K, which_matrix, normalize, threshold_at_zero)
+        def solve(sel, max_steps):
+            f = feats if sel is None else feats[sel]
+            return spectral.affinity_eigs(f, K, which_matrix, normalize, threshold_at_zero, max_steps=max_steps)
     else:
         rgb_lr, lr_size = None, None
         sizes = utils.get_image_sizes(data_dicts[0])
@@ -126,29 +194,32 @@ def _eigs_for_group(data_dicts: List[dict], K: int, images_root, which_features,
                 normalize = False
             feats = spectral.upsample_bilinear(feats, H_patch, W_patch, H_lr, W_lr)
         if image_color_lambda > 0:
-            lr = [_load_image_lr(images_root, d["file"][:-4], W_lr, H_lr) for d in data_dicts]
-            rgb_lr = torch.from_numpy(np.stack(lr).reshape(len(lr), H_lr * W_lr, 3).astype(np.float32)).to(dev)
+            rgb_lr = _color_inputs(images_root, [d["file"][:-4] for d in data_dicts], W_lr, H_lr, which_color_matrix, dev)
             lr_size = (H_lr, W_lr)
-        evals, evecs, info, _ = spectral.laplacian_eigs(feats, K, normalize, threshold_at_zero, lapnorm, rgb_lr,
-                                                        lr_size, image_color_lambda)
-    evals, evecs, info = evals.cpu(), evecs.cpu(), info.cpu()
-    bad = (info[:, 1] == 0).nonzero().flatten().tolist()
-    if bad:
-        print(f"Warning: eigensolver did not reach its tolerance for {[data_dicts[i]['id'] for i in bad]}")
+
+        def solve(sel, max_steps):
+            f = feats if sel is None else feats[sel]
+            rgb = rgb_lr if (sel is None or rgb_lr is None) else rgb_lr[sel]
+            return spectral.laplacian_eigs(f, K, normalize, threshold_at_zero, lapnorm, rgb, lr_size, image_color_lambda,
+                                           max_steps=max_steps, which_color_matrix=which_color_matrix)[:3]
+    evals, evecs, info, failed = _solve_with_retry(solve, len(data_dicts), feats.shape[1])
+    if failed:
+        print(f"Warning: eigensolver did not converge for {[data_dicts[i]['id'] for i in failed]}; no file is written for them")
     if which_matrix == "affinity" and bool((info[:, 2] != 0).any()):
         print("Warning: a negative eigenvalue exceeds the K-th largest in magnitude; eigsh(which='LM') would pick it")
-    return evals, evecs
+    return evals, evecs, failed
+
+
+def _eigs_dict(which_matrix, evals_k: torch.Tensor, evecs_k: torch.Tensor) -> dict:
+    """extract.py:242. The 'affinity' branch of the reference keeps `eigenvalues` as the ascending numpy array eigsh
+    returned while the eigenvectors are flipped to descending order (extract.py:171-172); mirrored here."""
+    eigenvalues = evals_k.flip(0).numpy().copy() if which_matrix == "affinity" else evals_k.clone()
+    return {"eigenvalues": eigenvalues, "eigenvectors": evecs_k.clone()}
 
 
 def _save_eigs(output_file, which_matrix, evals_k: torch.Tensor, evecs_k: torch.Tensor):
-    """extract.py:242-244. The 'affinity' branch of the reference keeps `eigenvalues` as the ascending numpy array
-    eigsh returned while the eigenvectors are flipped to descending order (extract.py:171-172); mirrored here."""
-    if which_matrix == "affinity":
-        eigenvalues = evals_k.flip(0).numpy().copy()
-    else:
-        eigenvalues = evals_k.clone()
     Path(output_file).parent.mkdir(parents=True, exist_ok=True)
-    torch.save({"eigenvalues": eigenvalues, "eigenvectors": evecs_k.clone()}, str(output_file))
+    torch.save(_eigs_dict(which_matrix, evals_k, evecs_k), str(output_file))
 
 
 def _extract_eig(inp: Tuple[int, str], K: int, images_root: str, output_dir: str, which_matrix: str = "laplacian",
@@ -164,8 +235,11 @@ def _extract_eig(inp: Tuple[int, str], K: int, images_root: str, output_dir: str
         print(f"Skipping existing file {str(output_file)}")
         return
     _check_supported(which_matrix, which_color_matrix, image_color_lambda)
-    evals, evecs = _eigs_for_group([data_dict], K, images_root, which_features, normalize, lapnorm, threshold_at_zero,
-                                   image_downsample_factor, image_color_lambda, _device(), which_matrix)
+    evals, evecs, failed = _eigs_for_group([data_dict], K, images_root, which_features, normalize, lapnorm,
+                                           threshold_at_zero, image_downsample_factor, image_color_lambda, _device(),
+                                           which_matrix, which_color_matrix)
+    if failed:
+        raise _lib.DssError(f"eigensolver did not converge for {image_id}")
     _save_eigs(output_file, which_matrix, evals[0], evecs[0])
 
 
@@ -173,7 +247,8 @@ def extract_eigs(images_root: str, features_dir: str, output_dir: str, which_mat
                  which_color_matrix: str = "knn", which_features: str = "k", normalize: bool = True,
                  threshold_at_zero: bool = True, lapnorm: bool = True, K: int = 20,
                  image_downsample_factor: Optional[int] = None, image_color_lambda: float = 0.0,
-                 multiprocessing: int = 0, batch_size: int = 128, yes: Optional[bool] = None):
+                 multiprocessing: int = 0, batch_size: int = 128, yes: Optional[bool] = None,
+                 num_workers: Optional[int] = None, num_workers_out: int = 8):
     """
     Extracts eigenvalues from features.
 
@@ -191,59 +266,75 @@ def extract_eigs(images_root: str, features_dir: str, output_dir: str, which_mat
                   output_dir=output_dir, image_downsample_factor=image_downsample_factor,
                   image_color_lambda=image_color_lambda, lapnorm=lapnorm)
     print(kwargs)
+    if multiprocessing:
+        print(f"Note: multiprocessing={multiprocessing} is ignored: images are batched inside the GPU kernels "
+              f"({batch_size} per launch) instead of forked CPU workers")
     _check_supported(which_matrix, which_color_matrix, image_color_lambda)
     dev = _device()
     inputs = list(enumerate(sorted(Path(features_dir).iterdir())))
     import time
     start = time.time()
-    groups: dict = defaultdict(list)  # N -> [data_dict]
+    all_failed: List[str] = []
 
-    def flush(key):
-        dds = groups.pop(key, [])
-        if not dds:
-            return
-        evals, evecs = _eigs_for_group(dds, K, images_root, which_features, normalize, lapnorm, threshold_at_zero,
-                                       image_downsample_factor, image_color_lambda, dev, which_matrix)
-        for j, d in enumerate(dds):
-            _save_eigs(Path(output_dir) / f"{d['file'][:-4]}.pth", which_matrix, evals[j], evecs[j])
+    with io_pipeline.AsyncWriter(num_workers_out) as writer:
+        def flush(key, dds):
+            evals, evecs, failed = _eigs_for_group(dds, K, images_root, which_features, normalize, lapnorm,
+                                                   threshold_at_zero, image_downsample_factor, image_color_lambda, dev,
+                                                   which_matrix, which_color_matrix)
+            for j, d in enumerate(dds):
+                if j in failed:
+                    all_failed.append(d["id"])
+                    continue
+                writer.submit(_eigs_dict(which_matrix, evals[j], evecs[j]), Path(output_dir) / f"{d['file'][:-4]}.pth")
 
-    for index, features_file in inputs:
-        data_dict = torch.load(str(features_file), map_location="cpu")
-        image_id = data_dict["file"][:-4]
-        if (Path(output_dir) / f"{image_id}.pth").is_file():
-            print(f"Skipping existing file {str(Path(output_dir) / (image_id + '.pth'))}")
-            continue
-        key = (tuple(data_dict[which_features].shape[-2:]), tuple(data_dict["shape"]))
-        groups[key].append(data_dict)
-        if len(groups[key]) >= batch_size:
-            flush(key)
-    for key in list(groups.keys()):
-        flush(key)
+        batcher = _Batcher(batch_size, flush)
+        load = lambda i: torch.load(str(inputs[i][1]), map_location="cpu")   # noqa: E731  (file reads overlap on threads)
+        for data_dict in io_pipeline.ImagePrefetcher(load, range(len(inputs)), num_workers):
+            image_id = data_dict["file"][:-4]
+            if (Path(output_dir) / f"{image_id}.pth").is_file():
+                print(f"Skipping existing file {str(Path(output_dir) / (image_id + '.pth'))}")
+                continue
+            batcher.add((tuple(data_dict[which_features].shape[-2:]), tuple(data_dict["shape"])), data_dict)
+        batcher.finish()
     print(f"Finished in {time.time() - start:.1f}s")
+    if all_failed:
+        raise _lib.DssError(f"eigensolver did not converge for {len(all_failed)} image(s): {all_failed[:8]} -- their files "
+                            "were not written (all other outputs were)")
 
 
-def _extract_single_region_segmentations(inp, threshold: float, output_dir: str):
-    """Worker with the reference's signature (extract.py:364-390): eigenvector 1 > threshold on the patch grid -> PNG."""
+# ---------------------------------------------------------------------------------------------------------------
+# Segmentations: device kernels on batches of eigenvector files
+def _png_writer_pool(num_threads: int):
+    from concurrent.futures import ThreadPoolExecutor
+    return ThreadPoolExecutor(max(1, num_threads), thread_name_prefix="dss-png")
+
+
+def _save_png(arr_u8: np.ndarray, path: str):
     from PIL import Image
-    index, (feature_path, eigs_path) = inp
-    data_dict = torch.load(feature_path, map_location="cpu")
-    data_dict.update(torch.load(eigs_path, map_location="cpu", weights_only=False))
-    id = Path(data_dict["id"])
-    output_file = str(Path(output_dir) / f"{id}.png")
-    if Path(output_file).is_file():
-        print(f"Skipping existing file {str(output_file)}")
-        return
-    B, C, H, W, P, H_patch, W_patch, H_pad, W_pad = utils.get_image_sizes(data_dict)
-    eigenvector = data_dict["eigenvectors"][1].numpy()  # smallest non-zero eigenvector
-    segmap = (eigenvector > threshold).reshape(H_patch, W_patch)
-    Image.fromarray(segmap).convert("L").save(output_file)
+    Image.fromarray(arr_u8, mode="L").save(path)
+
+
+def _paired_dicts(inputs, output_dir, num_workers):
+    """Loads (features, eigs) file pairs on threads, skipping pairs whose PNG exists (extract.py:300-304)."""
+    def load(i):
+        _, (feature_path, eigs_path) = inputs[i]
+        data_dict = torch.load(str(feature_path), map_location="cpu")
+        data_dict.update(torch.load(str(eigs_path), map_location="cpu", weights_only=False))
+        return data_dict
+    for data_dict in io_pipeline.ImagePrefetcher(load, range(len(inputs)), num_workers):
+        output_file = str(Path(output_dir) / f"{Path(data_dict['id'])}.png")
+        if Path(output_file).is_file():
+            print(f"Skipping existing file {str(output_file)}")
+            continue
+        yield data_dict, output_file
 
 
 def extract_single_region_segmentations(features_dir: str, eigs_dir: str, output_dir: str, threshold: float = 0.0,
-                                        multiprocessing: int = 0, yes: Optional[bool] = None):
+                                        multiprocessing: int = 0, yes: Optional[bool] = None, batch_size: int = 256,
+                                        num_workers: Optional[int] = None):
     """
-    First consumer of the eigs files, same command / file contract as the reference
-    (extract/extract.py:393-411): thresholds the Fiedler-like eigenvector of every image into a patch-grid mask.
+    Thresholds the Fiedler-like eigenvector of every image into a patch-grid mask (reference
+    extract/extract.py:364-411), same command / file contract; the threshold runs on the GPU for a batch of images.
 
     Example:
     python extract.py extract_single_region_segmentations \
@@ -253,64 +344,33 @@ def extract_single_region_segmentations(features_dir: str, eigs_dir: str, output
     """
     utils.make_output_dir(output_dir, assume_yes=yes)
     inputs = utils.get_paired_input_files(features_dir, eigs_dir)
-    utils.parallel_process(inputs, lambda inp: _extract_single_region_segmentations(inp, threshold, output_dir),
-                           multiprocessing)
+    dev = _device()
+    with _png_writer_pool(4) as pool:
+        def flush(key, items):
+            evecs = torch.stack([torch.as_tensor(d["eigenvectors"]) for d, _ in items]).to(dev)
+            masks = segment.threshold_masks(evecs, threshold, which=1).cpu().numpy()
+            for j, (d, output_file) in enumerate(items):
+                _, _, _, _, _, H_patch, W_patch, _, _ = utils.get_image_sizes(d)
+                pool.submit(_save_png, masks[j].reshape(H_patch, W_patch).copy(), output_file)
 
-
-def _extract_multi_region_segmentations(inp, adaptive: bool, non_adaptive_num_segments: int, infer_bg_index: bool,
-                                        kmeans_baseline: bool, output_dir: str, num_eigenvectors: int,
-                                        random_state: Optional[int] = None):
-    """Worker with the reference's signature (extract.py:283-349): K-means on the non-constant eigenvectors (or on the
-    raw features, ``kmeans_baseline``) of one image -> label map on the patch grid, background label swapped to 0.
-
-    The clustering is scikit-learn's KMeans exactly as in the reference (unseeded there; ``random_state`` is an
-    extension, None = reference behaviour). It runs on the host: N <= a few thousand points in <= K dimensions.
-    """
-    from PIL import Image
-    from sklearn.cluster import KMeans
-    index, (feature_path, eigs_path) = inp
-    data_dict = torch.load(feature_path, map_location="cpu")
-    data_dict.update(torch.load(eigs_path, map_location="cpu", weights_only=False))
-    id = Path(data_dict["id"])
-    output_file = str(Path(output_dir) / f"{id}.png")
-    if Path(output_file).is_file():
-        print(f"Skipping existing file {str(output_file)}")
-        return
-    B, C, H, W, P, H_patch, W_patch, H_pad, W_pad = utils.get_image_sizes(data_dict)
-    if adaptive:   # number of segments = position of the largest eigengap (the gap after the constant vector excluded)
-        by_gap = np.argsort(np.diff(data_dict["eigenvalues"].numpy()))[::-1]
-        n_clusters = by_gap[by_gap != 0][0] + 1
-    else:
-        n_clusters = non_adaptive_num_segments
-    kmeans = KMeans(n_clusters=n_clusters) if random_state is None else KMeans(n_clusters=n_clusters,
-                                                                                random_state=random_state)
-    if kmeans_baseline:
-        clusters = kmeans.fit_predict(data_dict["k"].squeeze().numpy())
-    else:
-        clusters = kmeans.fit_predict(data_dict["eigenvectors"][1:1 + num_eigenvectors].numpy().T)
-    if clusters.size == H_patch * W_patch:
-        segmap = clusters.reshape(H_patch, W_patch)
-    elif clusters.size == H_patch * W_patch * 4:     # eigenvectors of the image_downsample_factor = P/2 mode
-        segmap = clusters.reshape(H_patch * 2, W_patch * 2)
-    else:
-        raise ValueError(f"{clusters.size} labels do not fit a {H_patch} x {W_patch} patch grid")
-    if infer_bg_index:   # the label owning most of the border becomes 0 (labels 0 and bg are swapped)
-        labels, share = utils.get_border_fraction(segmap)
-        bg_index = labels[np.argmax(share)].item()
-        bg_region, zero_region = segmap == bg_index, segmap == 0
-        segmap[bg_region] = 0
-        segmap[zero_region] = bg_index
-    Image.fromarray(segmap).convert("L").save(output_file)
+        batcher = _Batcher(batch_size, flush)
+        for d, output_file in _paired_dicts(inputs, output_dir, num_workers):
+            batcher.add(tuple(torch.as_tensor(d["eigenvectors"]).shape), (d, output_file))
+        batcher.finish()
 
 
 def extract_multi_region_segmentations(features_dir: str, eigs_dir: str, output_dir: str, adaptive: bool = False,
                                        non_adaptive_num_segments: int = 4, infer_bg_index: bool = True,
                                        kmeans_baseline: bool = False, num_eigenvectors: int = 1_000_000,
                                        multiprocessing: int = 0, random_state: Optional[int] = None,
-                                       yes: Optional[bool] = None):
+                                       yes: Optional[bool] = None, batch_size: int = 256,
+                                       num_workers: Optional[int] = None):
     """
-    Second consumer of the eigs files, same command / file contract as the reference
-    (extract/extract.py:352-376).
+    K-means on the non-constant eigenvectors (or on the raw features, ``kmeans_baseline``) of every image -> label map
+    on the patch grid, background label swapped to 0 (reference extract/extract.py:283-376), same command / file
+    contract. The clustering is the batched device K-means of csrc/segment.cu (k-means++ / Lloyd with scikit-learn's
+    stopping rules); the reference's KMeans is unseeded, so label NUMBERS differ from run to run there and only the
+    partition is comparable. ``random_state`` seeds the device generator (default 0: reproducible).
 
     Example:
     python extract.py extract_multi_region_segmentations \
@@ -320,63 +380,167 @@ def extract_multi_region_segmentations(features_dir: str, eigs_dir: str, output_
     """
     utils.make_output_dir(output_dir, assume_yes=yes)
     inputs = utils.get_paired_input_files(features_dir, eigs_dir)
-    utils.parallel_process(
-        inputs, lambda inp: _extract_multi_region_segmentations(inp, adaptive, non_adaptive_num_segments, infer_bg_index,
-                                                                kmeans_baseline, output_dir, num_eigenvectors,
-                                                                random_state), multiprocessing)
-
-
-def extract_all(images_list: str, images_root: Optional[str], model_name: str, features_dir: Optional[str],
-                eigs_dir: str, K: int = 20, batch_size: int = 16, which_block: int = -1, normalize: bool = True,
-                threshold_at_zero: bool = True, lapnorm: bool = True, image_color_lambda: float = 0.0,
-                checkpoint: Optional[str] = None, seed: int = 0, yes: Optional[bool] = None):
-    """Fused extract_features + extract_eigs: features never leave the GPU between the two stages. Writes the eigs
-    files (and, if features_dir is given, the features files) in the reference's layouts."""
-    if features_dir:
-        utils.make_output_dir(features_dir, assume_yes=yes)
-    utils.make_output_dir(eigs_dir, assume_yes=yes)
-    model_name = model_name.lower()
     dev = _device()
-    model, _, patch_size, _ = utils.get_model(model_name, checkpoint=checkpoint, seed=seed, device=dev)
+    seed = 0 if random_state is None else int(random_state)
+    with _png_writer_pool(4) as pool:
+        def flush(key, items):
+            dicts = [d for d, _ in items]
+            ks = [segment.adaptive_num_clusters(torch.as_tensor(d["eigenvalues"]).numpy()) if adaptive
+                  else non_adaptive_num_segments for d in dicts]
+            _, _, _, _, _, H_patch, W_patch, _, _ = utils.get_image_sizes(dicts[0])
+            if kmeans_baseline:
+                pts = torch.stack([d["k"].squeeze() for d in dicts]).to(dev)
+                n_pts, layout = pts.shape[1], "features"
+            else:
+                pts = torch.stack([torch.as_tensor(d["eigenvectors"])[1:1 + num_eigenvectors] for d in dicts]).to(dev)
+                n_pts, layout = pts.shape[2], "eigenvectors"
+            if n_pts == H_patch * W_patch:     # extract.py:328-333
+                grid = (H_patch, W_patch)
+            elif n_pts == H_patch * W_patch * 4:
+                grid = (H_patch * 2, W_patch * 2)
+            else:
+                raise ValueError(f"{n_pts} labels do not fit a {H_patch} x {W_patch} patch grid")
+            labels, _, _ = segment.kmeans_labels(pts, ks, grid, infer_bg_index, layout, seed)
+            labels = labels.cpu().numpy()
+            for j, (_, output_file) in enumerate(items):
+                pool.submit(_save_png, labels[j].reshape(grid).copy(), output_file)
+
+        batcher = _Batcher(batch_size, flush)
+        for d, output_file in _paired_dicts(inputs, output_dir, num_workers):
+            key = (tuple(torch.as_tensor(d["eigenvectors"]).shape), tuple(d["k"].shape), tuple(d["shape"]))
+            batcher.add(key, (d, output_file))
+        batcher.finish()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def extract_bbox_features(images_root: str, bbox_file: str, model_name: str, output_file: str,
+                          checkpoint: Optional[str] = None, seed: Optional[int] = None, random_init: bool = False,
+                          batch_size: int = 64):
+    """
+    DINO CLS embedding of every bounding-box crop (reference extract/extract.py:500-544), same command / file
+    contract: each dict of ``bbox_file`` gains 'features' [n_boxes, d] fp32. Crops of equal size are batched.
+
+    Example:
+        python extract.py extract_bbox_features \
+            --model_name dino_vits16 \
+            --images_root "./data/VOC2012/images" \
+            --bbox_file "./data/VOC2012/multi_region_bboxes/fixed/bboxes_e2_d5.pth" \
+            --output_file "./data/VOC2012/multi_region_bboxes/fixed/bbox_features_e2_d5.pth" \
+    """
+    from PIL import Image
+    bbox_list = torch.load(bbox_file, weights_only=False)
+    total_num_boxes = sum(len(d["bboxes"]) for d in bbox_list)
+    print(f"Loaded bounding box list. There are {total_num_boxes} total bounding boxes.")
+    dev = _device()
+    model, _, patch_size, _ = utils.get_model(model_name.lower(), checkpoint=checkpoint, seed=seed, device=dev,
+                                              random_init=random_init)
+    feats: Dict[Tuple[int, int], torch.Tensor] = {}   # (image row, box row) -> [d]
+
+    def flush(shape_key, items):
+        batch = torch.stack([it[0] for it in items]).to(dev)
+        cls = model.forward_cls(batch).cpu()
+        for j, (_, where) in enumerate(items):
+            feats[where] = cls[j].clone()
+
+    batcher = _Batcher(batch_size, flush)
+    for bi, bbox_dict in enumerate(bbox_list):
+        image_filename = str(Path(images_root) / f"{bbox_dict['id']}.jpg")
+        image = torch.from_numpy(np.ascontiguousarray(np.asarray(Image.open(image_filename).convert("RGB"))))
+        for ji, (xmin, ymin, xmax, ymax) in enumerate(bbox_dict["bboxes_original_resolution"]):
+            crop = image[ymin:ymax, xmin:xmax].contiguous()          # image[:, :, ymin:ymax, xmin:xmax] at :539
+            if crop.shape[0] < patch_size or crop.shape[1] < patch_size:
+                raise ValueError(f"{bbox_dict['id']}: box {(xmin, ymin, xmax, ymax)} is smaller than one patch")
+            batcher.add((int(crop.shape[0]), int(crop.shape[1])), (crop, (bi, ji)))
+    batcher.finish()
+    for bi, bbox_dict in enumerate(bbox_list):
+        bbox_dict["features"] = torch.stack([feats[(bi, ji)] for ji in range(len(bbox_dict["bboxes"]))], dim=0)
+    torch.save(bbox_list, output_file)
+    print(f"Saved features to {output_file}")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def extract_all(images_list: str, images_root: Optional[str], model_name: str, features_dir: Optional[str],
+                eigs_dir: str, K: int = 20, batch_size: int = 64, which_block: int = -1, normalize: bool = True,
+                threshold_at_zero: bool = True, lapnorm: bool = True, image_color_lambda: float = 0.0,
+                which_color_matrix: str = "knn", checkpoint: Optional[str] = None, seed: Optional[int] = None,
+                random_init: bool = False, yes: Optional[bool] = None, single_region_dir: Optional[str] = None,
+                multi_region_dir: Optional[str] = None, non_adaptive_num_segments: int = 4, adaptive: bool = False,
+                infer_bg_index: bool = True, threshold: float = 0.0, num_workers: Optional[int] = None,
+                num_workers_out: int = 8):
+    """Fused extract_features + extract_eigs (+ the two segmentation commands): features and eigenvectors never leave
+    the GPU between the stages. Writes the eigs files and, if the directories are given, the features files and the
+    single- / multi-region segmentation PNGs, all in the reference's layouts. Decoding, pinned staging and the file
+    writers run on threads (io_pipeline.py)."""
+    for dname in (features_dir, eigs_dir, single_region_dir, multi_region_dir):
+        if dname:
+            utils.make_output_dir(dname, assume_yes=yes)
+    model_name = model_name.lower()
+    _check_supported("laplacian", which_color_matrix, image_color_lambda)
+    dev = _device()
+    model, _, patch_size, _ = utils.get_model(model_name, checkpoint=checkpoint, seed=seed, device=dev,
+                                              random_init=random_init)
     filenames = Path(images_list).read_text().splitlines()
     dataset = utils.ImagesDataset(filenames=filenames, images_root=images_root)
-    pending: dict = defaultdict(list)
+    rings: Dict[tuple, io_pipeline.PinnedRing] = {}
+    all_failed: List[str] = []
 
-    def flush(key):
-        items = pending.pop(key, [])
-        if not items:
-            return
-        H, W = key
-        batch = torch.stack([it[0] for it in items]).pin_memory().to(dev, non_blocking=True)
-        k = model.forward_k(batch, which_block=which_block)
-        rgb_lr, lr_size = None, None
-        Hp, Wp = H // patch_size, W // patch_size
-        if image_color_lambda > 0:
-            lr = [_load_image_lr(images_root, it[1][:-4], Wp, Hp) for it in items]
-            rgb_lr = torch.from_numpy(np.stack(lr).reshape(len(lr), Hp * Wp, 3).astype(np.float32)).to(dev)
-            lr_size = (Hp, Wp)
-        evals, evecs, info, _ = spectral.laplacian_eigs(k, K, normalize, threshold_at_zero, lapnorm, rgb_lr, lr_size,
-                                                        image_color_lambda)
-        evals, evecs = evals.cpu(), evecs.cpu()
-        k_cpu = k.cpu() if features_dir else None
-        for j, (_, file, index) in enumerate(items):
-            if features_dir:
-                fd = _feature_dict(k_cpu[j:j + 1].clone(), index, file, model_name, patch_size, H, W)
-                torch.save(fd, str(Path(features_dir) / f"{fd['id']}.pth"))
-            out = Path(eigs_dir) / f"{file[:-4]}.pth"
-            out.parent.mkdir(parents=True, exist_ok=True)
-            torch.save({"eigenvalues": evals[j].clone(), "eigenvectors": evecs[j].clone()}, str(out))
+    with io_pipeline.AsyncWriter(num_workers_out) as writer, _png_writer_pool(2) as png_pool:
+        def flush(key, items):
+            H, W = key
+            ring = rings.get(key)
+            if ring is None:
+                ring = rings[key] = io_pipeline.PinnedRing(key, max(1, int(batch_size)), dev)
+            slot, host = ring.stage([it[0] for it in items])
+            k = model.forward_k(ring.to_device(slot, host), which_block=which_block)
+            Hp, Wp = H // patch_size, W // patch_size
+            rgb_lr, lr_size = None, None
+            if image_color_lambda > 0:
+                rgb_lr = _color_inputs(images_root, [it[1][:-4] for it in items], Wp, Hp, which_color_matrix, dev)
+                lr_size = (Hp, Wp)
+            kept = {}
 
-    for i in range(len(dataset)):
-        file = dataset.filenames[i]
-        if (Path(eigs_dir) / f"{file[:-4]}.pth").is_file():
-            print(f"Skipping existing file {str(Path(eigs_dir) / (file[:-4] + '.pth'))}")
-            continue
-        image, file, index = dataset[i]
-        key = (int(image.shape[0]), int(image.shape[1]))
-        pending[key].append((image, file, index))
-        if len(pending[key]) >= max(1, int(batch_size)):
-            flush(key)
-    for key in list(pending.keys()):
-        flush(key)
+            def solve(sel, max_steps):
+                f = k if sel is None else k[sel]
+                rgb = rgb_lr if (sel is None or rgb_lr is None) else rgb_lr[sel]
+                out = spectral.laplacian_eigs(f, K, normalize, threshold_at_zero, lapnorm, rgb, lr_size, image_color_lambda,
+                                              max_steps=max_steps, which_color_matrix=which_color_matrix)
+                if sel is None:
+                    kept["evecs"], kept["evals"] = out[1], out[0]
+                return out[:3]
+            evals, evecs, info, failed = _solve_with_retry(solve, len(items), Hp * Wp)
+            masks = labels = None
+            if single_region_dir:
+                masks = segment.threshold_masks(kept["evecs"], threshold, which=1).cpu().numpy()
+            if multi_region_dir:
+                ks = [segment.adaptive_num_clusters(evals[j].numpy()) if adaptive else non_adaptive_num_segments
+                      for j in range(len(items))]
+                labels = segment.kmeans_labels(kept["evecs"][:, 1:], ks, (Hp, Wp), infer_bg_index)[0].cpu().numpy()
+            k_cpu = k.cpu() if features_dir else None
+            for j, (_, file, index) in enumerate(items):
+                if j in failed:
+                    all_failed.append(file)
+                    continue
+                if features_dir:
+                    fd = _feature_dict(k_cpu[j:j + 1].clone(), index, file, model_name, patch_size, H, W)
+                    writer.submit(fd, Path(features_dir) / f"{fd['id']}.pth")
+                writer.submit({"eigenvalues": evals[j].clone(), "eigenvectors": evecs[j].clone()},
+                              Path(eigs_dir) / f"{file[:-4]}.pth")
+                if masks is not None:
+                    png_pool.submit(_save_png, masks[j].reshape(Hp, Wp).copy(), str(Path(single_region_dir) / f"{Path(file).stem}.png"))
+                if labels is not None:
+                    png_pool.submit(_save_png, labels[j].reshape(Hp, Wp).copy(), str(Path(multi_region_dir) / f"{Path(file).stem}.png"))
+
+        batcher = _Batcher(batch_size, flush)
+        todo = []
+        for i in range(len(dataset)):
+            file = dataset.filenames[i]
+            if (Path(eigs_dir) / f"{file[:-4]}.pth").is_file():
+                print(f"Skipping existing file {str(Path(eigs_dir) / (file[:-4] + '.pth'))}")
+            else:
+                todo.append(i)
+        for image, file, index in io_pipeline.ImagePrefetcher(dataset.__getitem__, todo, num_workers):
+            batcher.add((int(image.shape[0]), int(image.shape[1])), (image, file, index))
+        batcher.finish()
     print(f"Saved eigs to {eigs_dir}")
+    if all_failed:
+        raise _lib.DssError(f"eigensolver did not converge for {len(all_failed)} image(s): {all_failed[:8]}")

@@ -1,0 +1,147 @@
+"""Host I/O around the GPU stages. The reference decodes with 8 DataLoader worker processes
+(extract/extract.py:60) and writes one .pth per image synchronously (:113, :244); at the rates the kernels run
+(thousands of images per second) both would dominate. Here:
+
+  * ``ImagePrefetcher``  decodes JPEG/PNG files on a thread pool (cv2 / PIL release the GIL while decoding) with a
+                          bounded look-ahead, yielding items in order;
+  * ``PinnedRing``       stages equally shaped uint8 images into a small ring of page-locked batches so that the
+                          host->device copy is asynchronous and the decoder never waits for the GPU;
+  * ``AsyncWriter``      runs ``torch.save`` (same dict layouts, so ``torch.load`` consumers are unaffected) on writer
+                          threads; ``close()`` waits for them and re-raises the first error.
+
+Pure host code: nothing here touches the device except ``PinnedRing.to_device``'s copy."""
+from __future__ import annotations
+
+import os
+import queue
+import threading
+from collections import deque
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+from typing import Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import torch
+
+
+def default_workers(cap: int = 32) -> int:
+    return max(1, min(cap, (os.cpu_count() or 2) - 1))
+
+
+class ImagePrefetcher:
+    """Iterates ``load(i)`` for i in ``indices`` in order, keeping up to ``lookahead`` loads in flight on a thread pool."""
+
+    def __init__(self, load: Callable[[int], object], indices: Sequence[int], num_workers: Optional[int] = None,
+                 lookahead: Optional[int] = None):
+        self.load, self.indices = load, list(indices)
+        self.num_workers = num_workers if num_workers is not None else default_workers()
+        self.lookahead = lookahead if lookahead is not None else 4 * max(1, self.num_workers)
+
+    def __len__(self):
+        return len(self.indices)
+
+    def __iter__(self) -> Iterator:
+        if self.num_workers <= 0:
+            for i in self.indices:
+                yield self.load(i)
+            return
+        with ThreadPoolExecutor(self.num_workers, thread_name_prefix="dss-decode") as pool:
+            pending: deque = deque()
+            it = iter(self.indices)
+            try:
+                for i in it:
+                    pending.append(pool.submit(self.load, i))
+                    if len(pending) >= self.lookahead:
+                        yield pending.popleft().result()
+                while pending:
+                    yield pending.popleft().result()
+            finally:
+                for f in pending:
+                    f.cancel()
+
+
+class PinnedRing:
+    """Ring of page-locked uint8 batches [slots][capacity, H, W, 3] for one image shape. ``stage`` copies decoded images
+    into the next slot (host memcpy), ``to_device`` starts the asynchronous H2D copy and returns the device batch; a
+    slot is reused only after the copy that read it has completed (tracked with a CUDA event)."""
+
+    def __init__(self, shape: Tuple[int, int], capacity: int, device, slots: int = 3):
+        H, W = shape
+        self.device = device
+        self.bufs = [torch.empty(capacity, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        self.events: List[Optional[torch.cuda.Event]] = [None] * slots
+        self.next = 0
+
+    def stage(self, images: Sequence[torch.Tensor]) -> Tuple[int, torch.Tensor]:
+        slot = self.next
+        self.next = (self.next + 1) % len(self.bufs)
+        if self.events[slot] is not None:
+            self.events[slot].synchronize()
+        buf = self.bufs[slot][:len(images)]
+        for j, im in enumerate(images):
+            buf[j].copy_(im)
+        return slot, buf
+
+    def to_device(self, slot: int, host_batch: torch.Tensor) -> torch.Tensor:
+        dev = host_batch.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.events[slot] = ev
+        return dev
+
+
+class AsyncWriter:
+    """``submit(obj, path)`` -> ``torch.save(obj, path)`` on one of ``num_threads`` writer threads (bounded queue)."""
+
+    def __init__(self, num_threads: int = 4, max_pending: int = 1024):
+        self.q: "queue.Queue" = queue.Queue(max_pending)
+        self.err: Optional[BaseException] = None
+        self.written = 0
+        self._lock = threading.Lock()
+        self.threads = [threading.Thread(target=self._run, name=f"dss-writer-{i}", daemon=True)
+                        for i in range(max(1, num_threads))]
+        for t in self.threads:
+            t.start()
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            obj, path = item
+            try:
+                if self.err is None:
+                    Path(path).parent.mkdir(parents=True, exist_ok=True)
+                    tmp = f"{path}.tmp{threading.get_ident()}"
+                    torch.save(obj, tmp)
+                    os.replace(tmp, path)   # a crash never leaves a truncated file for skip-if-exists to trust
+                    with self._lock:
+                        self.written += 1
+            except BaseException as e:  # noqa: BLE001  (reported by close())
+                self.err = e
+
+    def submit(self, obj, path) -> None:
+        if self.err is not None:
+            raise self.err
+        self.q.put((obj, str(path)))
+
+    def close(self) -> int:
+        for _ in self.threads:
+            self.q.put(None)
+        for t in self.threads:
+            t.join()
+        if self.err is not None:
+            raise self.err
+        return self.written
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.close()
+        else:   # do not mask the caller's exception
+            try:
+                self.close()
+            except BaseException:  # noqa: BLE001
+                pass
+        return False

@@ -57,10 +57,11 @@ class SpectralPipeline:
 
     def __init__(self, model_name: str = "dino_vits16", K: int = 5, device="cuda", state_dict=None, seed: int = 0,
                  vit_batch: int = 32, which_block: int = -1, normalize=True, threshold_at_zero=True, lapnorm=True,
-                 tol: float = 0.0, max_steps: int = 0):
+                 tol: float = 0.0, max_steps: int = 0, model: Optional[DinoViT] = None):
         self.device = torch.device(device)
-        self.model = DinoViT(model_name, state_dict if state_dict is not None else random_state_dict(model_name, seed),
-                             device=self.device)
+        # ``model``: share one weight handle between several pipelines (one per image shape: buffers are per pipeline)
+        self.model = model if model is not None else DinoViT(
+            model_name, state_dict if state_dict is not None else random_state_dict(model_name, seed), device=self.device)
         self.K, self.vit_batch, self.which_block = K, vit_batch, which_block
         self.normalize, self.threshold_at_zero, self.lapnorm = normalize, threshold_at_zero, lapnorm
         self.tol, self.max_steps = tol, max_steps
@@ -76,12 +77,15 @@ class SpectralPipeline:
         return b
 
     @torch.no_grad()
-    def run_device(self, images_u8: torch.Tensor, events: Optional[list] = None):
-        """images_u8 [B,H,W,3] already in HBM. `events[i]` (optional) gates ViT sub-batch i on its H2D copy."""
+    def run_device(self, images_u8: torch.Tensor, events: Optional[list] = None, slot: int = 0):
+        """images_u8 [B,H,W,3] already in HBM. `events[i]` (optional) gates ViT sub-batch i on its H2D copy. ``slot``
+        selects one of the feature buffers (the streaming driver alternates two so that the D2H copy of one batch's
+        features overlaps the next batch's compute)."""
         B, H, W, _ = images_u8.shape
         P, d = self.model.patch_size, self.model.dim
         N = (H // P) * (W // P)
-        feats = self._buf("feats", (B, N, d), torch.float32)
+        feats = self._buf(("feats", slot), (B, N, d), torch.float32)
+        self._bufs["feats"] = feats   # most recent features (parity checks read them)
         vb = self.vit_batch
         for i, s in enumerate(range(0, B, vb)):
             if events is not None:
@@ -121,13 +125,17 @@ class SpectralPipeline:
         return h_evals, h_evecs, h_info
 
     @torch.no_grad()
-    def run_host_pipelined(self, batches, copy_chunk: int = 32):
+    def run_host_pipelined(self, batches, copy_chunk: int = 32, features: bool = False):
         """Streaming form of run_host for a sequence of equally shaped HOST batches: the H2D copy of batch i+1 runs
-        on the copy stream while batch i is being computed, and the D2H of batch i completes while batch i+1 runs.
-        Yields (eigenvalues, eigenvectors, info) per batch, in order; the yielded tensors are pinned buffers that stay
-        valid until two further batches have been submitted."""
+        on the copy stream while batch i is being computed, and the D2H copies of batch i (on a third stream) complete
+        while batch i+1 runs. Yields (eigenvalues, eigenvectors, info[, features]) per batch, in order; the yielded
+        tensors are pinned buffers that stay valid until two further batches have been submitted. ``features=True``
+        also brings the K features [B, N, d] back (what extract_features writes to features/*.pth)."""
         cur = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_d2h_stream"):
+            self._d2h_stream = torch.cuda.Stream(self.device)
         done = [None, None]      # per slot: event recorded after the D2H of the batch that used the slot
+        keep = [None, None]      # per slot: device outputs kept alive until their D2H has completed
         pending = None           # (slot, outputs) of the previous batch
         for i, hb in enumerate(batches):
             assert not hb.is_cuda and hb.dtype == torch.uint8
@@ -135,7 +143,9 @@ class SpectralPipeline:
             B = hb.shape[0]
             dev_imgs = self._buf(("imgs", slot), tuple(hb.shape), torch.uint8)
             if done[slot] is not None:
-                self._copy_stream.wait_event(done[slot])   # the batch that used this slot two steps ago is finished
+                # the batch that used this slot two steps ago has been read back: its image / feature buffers are free
+                self._copy_stream.wait_event(done[slot])
+                cur.wait_event(done[slot])
             vb = self.vit_batch
             events = []
             with torch.cuda.stream(self._copy_stream):
@@ -146,23 +156,34 @@ class SpectralPipeline:
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)
                     events.append(ev)
-            evals, evecs, info = self.run_device(dev_imgs, events)
-            outs = (self._buf(("h_evals", slot), tuple(evals.shape), torch.float32, pinned=True),
+            evals, evecs, info = self.run_device(dev_imgs, events, slot=slot)
+            feats = self._bufs[("feats", slot)]
+            computed = torch.cuda.Event()
+            computed.record(cur)
+            outs = [self._buf(("h_evals", slot), tuple(evals.shape), torch.float32, pinned=True),
                     self._buf(("h_evecs", slot), tuple(evecs.shape), torch.float32, pinned=True),
-                    self._buf(("h_info", slot), tuple(info.shape), torch.int32, pinned=True))
-            outs[0].copy_(evals, non_blocking=True)
-            outs[1].copy_(evecs, non_blocking=True)
-            outs[2].copy_(info, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(cur)
+                    self._buf(("h_info", slot), tuple(info.shape), torch.int32, pinned=True)]
+            if features:
+                outs.append(self._buf(("h_feats", slot), tuple(feats.shape), torch.float32, pinned=True))
+            with torch.cuda.stream(self._d2h_stream):
+                self._d2h_stream.wait_event(computed)
+                outs[0].copy_(evals, non_blocking=True)
+                outs[1].copy_(evecs, non_blocking=True)
+                outs[2].copy_(info, non_blocking=True)
+                if features:
+                    outs[3].copy_(feats, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._d2h_stream)
             done[slot] = ev
+            keep[slot] = (evals, evecs, info)
             if pending is not None:
                 done[pending[0]].synchronize()
-                yield pending[1]
+                yield tuple(pending[1])
             pending = (slot, outs)
         if pending is not None:
             done[pending[0]].synchronize()
-            yield pending[1]
+            yield tuple(pending[1])
+        cur.wait_stream(self._d2h_stream)
 
     @staticmethod
     def launches_per_call(depth: int, which_block: int, n_vit_batches: int) -> int:

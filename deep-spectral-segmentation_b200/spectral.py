@@ -170,17 +170,59 @@ def affinity_eigs(feats: torch.Tensor, K: int, which_matrix: str = "affinity", n
     return evals, evecs, info
 
 
+RW_COEF = 900.0   # pymatting's _rw_laplacian hard-codes exp(-900 ||zi - zj||^2); its sigma argument (0.033) is unused
+
+
+@torch.no_grad()
+def rw_affinity_add(W: torch.Tensor, degree: Optional[torch.Tensor], rgb_u8: torch.Tensor, Hl: int, Wl: int,
+                    color_lambda: float, coef: float = RW_COEF) -> None:
+    """W [B, N, ldw] += lambda * random-walk colour affinity of the uint8 low-res images rgb_u8 [B, N, 3]
+    (which_color_matrix='rw', extract_utils.py:191-204); degree [B, N] is updated with the added row sums."""
+    _lib.require_cuda(W, "W")
+    assert rgb_u8.dtype == torch.uint8 and rgb_u8.is_cuda and rgb_u8.is_contiguous()
+    B, N, ldw = W.shape
+    assert N == Hl * Wl and tuple(rgb_u8.shape) == (B, N, 3)
+    with torch.cuda.device(W.device):
+        _lib.check(_lib.load().dss_rw_affinity_add(rgb_u8.data_ptr(), B, Hl, Wl, float(color_lambda), float(coef),
+                                                   W.data_ptr(), ldw, _lib.ptr(degree), _lib.stream_ptr(W.device)),
+                   "dss_rw_affinity_add")
+
+
 @torch.no_grad()
 def laplacian_eigs(feats: torch.Tensor, K: int, normalize=True, threshold_at_zero=True, lapnorm=True,
                    rgb_lr: Optional[torch.Tensor] = None, lr_size: Optional[Tuple[int, int]] = None,
-                   color_lambda: float = 0.0, tol: float = 0.0, max_steps: int = 0):
-    """which_matrix='laplacian' of the reference for a batch: feats [B,N,d] -> (eigenvalues [B,K], eigenvectors [B,K,N])."""
+                   color_lambda: float = 0.0, tol: float = 0.0, max_steps: int = 0, which_color_matrix: str = "knn"):
+    """which_matrix='laplacian' of the reference for a batch: feats [B,N,d] -> (eigenvalues [B,K], eigenvectors [B,K,N]).
+    rgb_lr: the low-resolution image of extract.py:199-204 -- fp32 [B,N,3] in [0,1] for 'knn', the uint8 pixels
+    [B,N,3] (before the /255) for 'rw'."""
     cc = None
     if color_lambda > 0:
         if rgb_lr is None or lr_size is None:
             raise ValueError("image_color_lambda > 0 needs the low-resolution image (rgb_lr, lr_size)")
-        cc = knn_color_counts(rgb_lr, lr_size[0], lr_size[1])
+        if which_color_matrix == "knn":
+            cc = knn_color_counts(rgb_lr, lr_size[0], lr_size[1])
+        elif which_color_matrix != "rw":
+            raise ValueError(f"unknown which_color_matrix={which_color_matrix!r}")
     deg = torch.empty(feats.shape[0], feats.shape[1], dtype=torch.float32, device=feats.device)
     W = affinity(feats, normalize, threshold_at_zero, cc, color_lambda, degree=deg)
+    if color_lambda > 0 and which_color_matrix == "rw":
+        rw_affinity_add(W, deg, rgb_lr, lr_size[0], lr_size[1], color_lambda)
     evals, evecs, info, resid = eigsh_laplacian(W, feats.shape[1], K, lapnorm, tol, max_steps, degree=deg)
     return evals, evecs, info, resid
+
+
+@torch.no_grad()
+def get_eigenvectors_from_features(feats: torch.Tensor, which_matrix: str = "laplacian", K: int = 2):
+    """Second caller of the eigensolver in the reference: object-localization/object_discovery.py:16-42
+    (``get_eigenvectors_from_features``: A = F F^T on the features AS GIVEN, relu, /max, degree, eigsh(D - A, sigma=0,
+    M=D) in float64, K=2, no sign rule). feats [N, d] CUDA -> (eigenvalues [K], eigenvectors [K, N]) on the device.
+    The sign of each vector is the library's (the reference returns ARPACK's arbitrary sign there)."""
+    if which_matrix == "affinity_torch":
+        raise RuntimeError("which_matrix='affinity_torch' calls torch.eig, which PyTorch removed (dead in the reference)")
+    if which_matrix == "affinity":
+        ev, vec, _ = affinity_eigs(feats[None], K, "affinity", normalize=False, threshold_at_zero=False)
+        return ev[0].flip(0), vec[0]          # the reference leaves eigsh's ascending values next to flipped vectors
+    if which_matrix == "laplacian":
+        ev, vec, _, _ = laplacian_eigs(feats[None], K, normalize=False, threshold_at_zero=True, lapnorm=True)
+        return ev[0], vec[0]
+    raise NotImplementedError(which_matrix)   # 'matting_laplacian' raises in the reference as well (:44-46)

@@ -66,7 +66,7 @@ def flat_param_order(name: str):
         keys += [p + s for s in ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
                                  "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias",
                                  "mlp.fc2.weight", "mlp.fc2.bias")]
-    return keys
+    return keys + ["norm.weight", "norm.bias"]
 
 
 class DinoViT:
@@ -99,7 +99,8 @@ class DinoViT:
                 for f, n in names.items():
                     setattr(blocks[l], f, dev[f"blocks.{l}.{n}"].data_ptr())
             w = _lib.VitWeights(dev["patch_embed.proj.weight"].data_ptr(), dev["patch_embed.proj.bias"].data_ptr(),
-                                dev["cls_token"].data_ptr(), dev["pos_embed"].data_ptr(), blocks)
+                                dev["cls_token"].data_ptr(), dev["pos_embed"].data_ptr(), blocks,
+                                dev["norm.weight"].data_ptr(), dev["norm.bias"].data_ptr())
             _lib.check(self.lib.dss_vit_load_weights(self._h, C.byref(w), _lib.stream_ptr(self.device)),
                        "dss_vit_load_weights")
             torch.cuda.current_stream(self.device).synchronize()
@@ -154,6 +155,21 @@ class DinoViT:
                                                        ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)),
                        "dss_vit_forward_tokens")
         return out
+
+    @torch.no_grad()
+    def forward_cls(self, images_u8: torch.Tensor) -> torch.Tensor:
+        """The model's own forward (upstream VisionTransformer.forward): all blocks, final norm, CLS token -> [B, d].
+        This is what the reference calls on bounding-box crops (extract.py:537-541)."""
+        img = self._check_images(images_u8)
+        B, H, W, _ = img.shape
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, H, W)
+            out = torch.empty(B, self.dim, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.dss_vit_forward_cls(self._h, img.data_ptr(), B, H, W, out.data_ptr(), ws.data_ptr(),
+                                                    ws.numel(), _lib.stream_ptr(self.device)), "dss_vit_forward_cls")
+        return out
+
+    __call__ = forward_cls
 
     def pos_embed(self, Hp: int, Wp: int) -> torch.Tensor:
         with torch.cuda.device(self.device):

@@ -80,6 +80,7 @@ typedef struct {
   const float* cls_token; /* [d] */
   const float* pos_embed; /* [1 + grid0*grid0, d] */
   const dss_vit_block_weights* blocks; /* host array of `depth` entries */
+  const float *norm_w, *norm_b; /* [d] final LayerNorm; may be NULL (only dss_vit_forward_cls needs them) */
 } dss_vit_weights;
 
 int dss_vit_create(const dss_vit_config* cfg, dss_vit_t** out);
@@ -100,6 +101,11 @@ int dss_vit_forward_k(dss_vit_t* h, const uint8_t* images_u8, int B, int H, int 
 /* Debug/parity hook: residual stream x [B, T, d] fp32 after `n_blocks` full blocks (T = N + 1, CLS first). */
 int dss_vit_forward_tokens(dss_vit_t* h, const uint8_t* images_u8, int B, int H, int W, int n_blocks, float* x_out,
                            void* ws, size_t ws_bytes, dss_stream_t stream);
+
+/* The model's own forward (upstream VisionTransformer.forward: all blocks, final LayerNorm, CLS token), which the
+ * reference calls on bounding-box crops (extract/extract.py:537-541, extract_bbox_features): cls_out [B, d] fp32. */
+int dss_vit_forward_cls(dss_vit_t* h, const uint8_t* images_u8, int B, int H, int W, float* cls_out, void* ws,
+                        size_t ws_bytes, dss_stream_t stream);
 
 /* Interpolated positional embedding [T, d] fp32 for an (Hp x Wp) patch grid, as upstream
  * VisionTransformer.interpolate_pos_encoding computes it (bicubic, scale (Hp+0.1)/grid0). Copied to out (device). */
@@ -193,6 +199,33 @@ int dss_eigsh_laplacian(const float* Wmat, const float* degree, int ldw, int B, 
  * F^ F^T, extract.py:160-163). Same workspace / info / resid conventions as dss_eigsh_laplacian. */
 int dss_eigsh_topk(const float* Amat, int lda, int B, int N, int K, float tol, int max_steps, float* evals,
                    float* evecs, int* info, float* resid, void* ws, size_t ws_bytes, dss_stream_t stream);
+
+/* Random-walk colour affinity (which_color_matrix='rw', extract_utils.py:191-204 -> pymatting _rw_laplacian with
+ * radius 1): Wmat[b, i, j] += float32(sum over the 3x3 clamped neighbourhood offsets that land on j of
+ * exp(-coef * ||z_i - z_j||^2)) * color_lambda, z = rgb_u8 / 255 in float64; the same amount is added to degree[b, i]
+ * (may be NULL). rgb_u8 [B, Hl*Wl, 3] is the low-resolution image of extract.py:199-204 BEFORE the /255.
+ * pymatting hard-codes coef = 900 (its sigma argument is unused); pass 1/sigma^2 for the textbook kernel. */
+int dss_rw_affinity_add(const uint8_t* rgb_u8, int B, int Hl, int Wl, float color_lambda, double coef, float* Wmat,
+                        int ldw, float* degree, dss_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Segmentations from the eigenvectors (replace extract/extract.py:283-349 and :364-390), fused after the eigensolve
+ * ------------------------------------------------------------------------------------------------------------ */
+/* mask[b, n] = 255 if evecs[b, which, n] > threshold else 0   (the 'L' image the reference saves; which = 1) */
+int dss_segment_threshold(const float* evecs, int B, int K, int N, int which, float threshold, uint8_t* mask,
+                          dss_stream_t stream);
+/* Batched K-means (k-means++ seeding, Lloyd, scikit-learn's stopping rules: tol * mean feature variance on the centre
+ * shift, strict label convergence, max_iter; empty clusters are re-seeded with the farthest point). One CTA per image.
+ * Point n of image b has coordinates points[b * image_stride + n * point_stride + j * dim_stride], j < dims -- the
+ * eigenvector embedding evecs[b, 1 + j, n] is (K*N, 1, N) from &evecs[b=0, 1, 0]; raw features [B, N, d] are (N*d, d, 1).
+ * n_clusters [B] int32 (device) gives k per image (the reference's adaptive mode), capped by max_clusters <= 64.
+ * If infer_bg_index, labels are taken on a grid_h x grid_w grid (grid_h * grid_w == N) and the label with the largest
+ * border share is swapped with 0 (extract_utils.py:124-135). labels [B, N] uint8; info [B, 2] = {iterations,
+ * converged}; inertia [B] (may be NULL). seed: counter-based generator (the reference's clustering is unseeded). */
+int dss_segment_kmeans(const float* points, long long image_stride, long long point_stride, long long dim_stride, int B,
+                       int N, int dims, const int* n_clusters, int max_clusters, int grid_h, int grid_w,
+                       int infer_bg_index, unsigned int seed, int max_iter, float tol, uint8_t* labels, int* info,
+                       float* inertia, dss_stream_t stream);
 
 /* Bilinear up-sampling of patch features (align_corners=False, as F.interpolate at extract.py:185-188):
  * feats [B, Hp*Wp, d] fp32 -> out [B, Hl*Wl, d] fp32. Used when image_downsample_factor != patch size. */

@@ -184,6 +184,15 @@ class DinoViT(nn.Module):
         raise AssertionError
 
     @torch.no_grad()
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """Upstream VisionTransformer.forward: all blocks, final LayerNorm, CLS token (B, d) -- what the reference's
+        extract_bbox_features calls on every crop (extract/extract.py:537-541)."""
+        x = self.prepare_tokens(images)
+        for blk in self.blocks:
+            x = blk(x)
+        return self.norm(x)[:, 0]
+
+    @torch.no_grad()
     def forward_tokens(self, images: torch.Tensor, n_blocks: int) -> torch.Tensor:
         """Residual stream after ``n_blocks`` full blocks (debug / per-layer parity)."""
         x = self.prepare_tokens(images)

@@ -79,6 +79,39 @@ def knn_affinity(image, n_neighbors=(20, 10), distance_weights=(2.0, 0.1), knn=k
     return scipy.sparse.csr_matrix((coo_data, (ij, ji)), (n, n))
 
 
+def rw_laplacian_values(image, sigma, r):
+    """pymatting.laplacian.rw_laplacian._rw_laplacian restated (pymatting is unpinned in requirements.txt:10 and not
+    installed here; restated from its published source, releases 1.0-1.1): for every pixel and every offset in
+    [-r, r]^2 the CLAMPED neighbour gets exp(-900 * ||z_i - z_j||^2). The published code hard-codes 900 and never
+    uses ``sigma`` (1 / 0.033^2 = 918); PARITY UNPINNED for this constant -- the CUDA entry point takes it as an
+    argument. Returns (values f8[m], i_inds i4[m], j_inds i4[m]), m = n (2r+1)^2, in pymatting's order."""
+    image = np.asarray(image, np.float64)
+    h, w = image.shape[:2]
+    n = h * w
+    ys, xs = np.mgrid[0:h, 0:w]
+    vals, ii, jj = [], [], []
+    for dy in range(-r, r + 1):
+        for dx in range(-r, r + 1):
+            x2 = np.clip(xs + dx, 0, w - 1)
+            y2 = np.clip(ys + dy, 0, h - 1)
+            diff = image[ys, xs] - image[y2, x2]
+            nrm = np.sqrt((diff * diff).sum(-1))
+            vals.append(np.exp(-900 * nrm ** 2))
+            ii.append(xs + ys * w)
+            jj.append(x2 + y2 * w)
+    # pymatting's loop order is (y, x, dy, dx): offsets vary fastest
+    order = lambda a: np.stack(a, axis=-1).reshape(n * (2 * r + 1) ** 2)
+    return order(vals), order(ii).astype(np.int32), order(jj).astype(np.int32)
+
+
+def rw_affinity(image, sigma=0.033, radius=1, rw=rw_laplacian_values):
+    """extract_utils.py:191-204 restated. image (h, w, 3) float64 in [0,1] -> csr (n, n) float64 (duplicates summed)."""
+    h, w = image.shape[:2]
+    n = h * w
+    values, i_inds, j_inds = rw(image, sigma, radius)
+    return scipy.sparse.csr_matrix((values, (i_inds, j_inds)), shape=(n, n))
+
+
 def get_diagonal(W, threshold: float = 1e-12):
     """extract_utils.py:207-220 restated."""
     D = row_sum(W)
@@ -103,7 +136,7 @@ def sign_rule_(eigenvectors: torch.Tensor) -> torch.Tensor:
 
 
 def affinity_matrices(feats: torch.Tensor, normalize=True, threshold_at_zero=True, image_lr=None,
-                      image_color_lambda=0.0, knn=knn_exact):
+                      image_color_lambda=0.0, knn=knn_exact, which_color_matrix="knn"):
     """extract.py:148,191-222 restated -> (W_comb float32 (n,n) ndarray, D_comb float32 dense diag (n,n))."""
     feats = feats.squeeze()
     if normalize:
@@ -114,7 +147,12 @@ def affinity_matrices(feats: torch.Tensor, normalize=True, threshold_at_zero=Tru
     W_feat = W_feat / W_feat.max()
     W_feat = W_feat.cpu().numpy()
     if image_color_lambda > 0:
-        W_lr = knn_affinity(image_lr, knn=knn)
+        if which_color_matrix == "knn":
+            W_lr = knn_affinity(image_lr, knn=knn)
+        elif which_color_matrix == "rw":
+            W_lr = rw_affinity(image_lr)
+        else:
+            raise ValueError(which_color_matrix)   # the reference leaves W_lr undefined here (UnboundLocalError)
         W_color = np.array(W_lr.todense().astype(np.float32))
     else:
         W_color = 0
@@ -132,7 +170,7 @@ def upsample_features(feats: torch.Tensor, grid, lr_size) -> torch.Tensor:
 
 def extract_eig(feats: torch.Tensor, K: int, which_matrix="laplacian", normalize=True, lapnorm=True,
                 threshold_at_zero=True, image_lr=None, image_color_lambda=0.0, knn=knn_exact, rng_seed=None,
-                grid=None, lr_size=None):
+                grid=None, lr_size=None, which_color_matrix="knn", stats=None):
     """The arithmetic of reference ``_extract_eig`` from a feature tensor to (eigenvalues, eigenvectors).
 
     ``feats`` is the (1, N, d) / (N, d) float32 ``data_dict['k']``; ``image_lr`` the (H_lr, W_lr, 3) float64 /255
@@ -162,17 +200,29 @@ def extract_eig(feats: torch.Tensor, K: int, which_matrix="laplacian", normalize
                 feats = F.normalize(feats, p=2, dim=-1)
                 normalize = False
             feats = upsample_features(feats, grid, lr_size)
-        W_comb, D_comb = affinity_matrices(feats, normalize, threshold_at_zero, image_lr, image_color_lambda, knn)
+        W_comb, D_comb = affinity_matrices(feats, normalize, threshold_at_zero, image_lr, image_color_lambda, knn,
+                                           which_color_matrix)
+        # ``stats`` (optional dict) records which route the reference's try/except took: D - W is singular, so its
+        # float32 LU can hit an exactly-zero pivot; the shift-invert solve then yields NaN/inf, ARPACK raises and the
+        # reference falls back to which='SM' (extract.py:226-229)
         if lapnorm:
             try:
                 eigenvalues, eigenvectors = eigsh(D_comb - W_comb, k=K, sigma=0, which="LM", M=D_comb, **kw)
+                if stats is not None:
+                    stats["route"] = "shift-invert"
             except Exception:
                 eigenvalues, eigenvectors = eigsh(D_comb - W_comb, k=K, which="SM", M=D_comb, **kw)
+                if stats is not None:
+                    stats["route"] = "SM-fallback"
         else:
             try:
                 eigenvalues, eigenvectors = eigsh(D_comb - W_comb, k=K, sigma=0, which="LM", **kw)
+                if stats is not None:
+                    stats["route"] = "shift-invert"
             except Exception:
                 eigenvalues, eigenvectors = eigsh(D_comb - W_comb, k=K, which="SM", **kw)
+                if stats is not None:
+                    stats["route"] = "SM-fallback"
         eigenvalues, eigenvectors = torch.from_numpy(eigenvalues), torch.from_numpy(eigenvectors.T).float()
     else:
         raise ValueError(which_matrix)
@@ -200,3 +250,26 @@ def eigh_f64(feats: torch.Tensor, K: int, normalize=True, lapnorm=True, threshol
     else:
         vals, vecs = scipy.linalg.eigh(L, subset_by_index=[0, K - 1])
     return vals, vecs.T
+
+
+def eigs_from_affinity(W_feat: np.ndarray, K: int, lapnorm: bool = True, rng_seed=None, stats=None):
+    """extract.py:216-240 from the point where the feature affinity has come back from the GPU (``W_feat.cpu().numpy()``,
+    :195): combine (no colour term), degree, dense diag, eigsh with the SM fallback, sign rule. This is the CPU half
+    of the reference AS SHIPPED (GPU matmul + CPU eigsh); bench.py times it for the `as_shipped` baseline."""
+    import time
+    kw = {} if rng_seed is None else {"rng": np.random.default_rng(rng_seed)}
+    t0 = time.perf_counter()
+    W_comb = W_feat + 0 * 0.0
+    D_comb = np.array(get_diagonal(W_comb).todense())
+    t1 = time.perf_counter()
+    try:
+        eigenvalues, eigenvectors = eigsh(D_comb - W_comb, k=K, sigma=0, which="LM", M=D_comb if lapnorm else None, **kw)
+        route = "shift-invert"
+    except Exception:
+        eigenvalues, eigenvectors = eigsh(D_comb - W_comb, k=K, which="SM", M=D_comb if lapnorm else None, **kw)
+        route = "SM-fallback"
+    t2 = time.perf_counter()
+    if stats is not None:
+        stats.update(route=route, degree_s=t1 - t0, eigsh_s=t2 - t1)
+    eigenvectors = sign_rule_(torch.from_numpy(eigenvectors.T).float())
+    return torch.from_numpy(eigenvalues), eigenvectors

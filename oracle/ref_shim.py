@@ -9,6 +9,7 @@ are replaced by inert stubs *before* ``import extract``:
   fire.Fire, accelerate.Accelerator, skimage.morphology.binary_{dilation,erosion}  -> never called on this path
   pymatting.util.util.row_sum    -> A.dot(ones)           (published behaviour; used at extract_utils.py:217)
   pymatting.util.kdtree.knn      -> exact KNN stand-in    (used at extract_utils.py:177)
+  pymatting.laplacian.rw_laplacian._rw_laplacian -> restated stencil weights (used at extract_utils.py:194,202)
 With no GPU, ``Tensor.cuda`` (extract.py:146) is made a no-op so the matmul runs on the CPU in float32.
 """
 from __future__ import annotations
@@ -71,6 +72,8 @@ def load_reference():
         _stub("pymatting.util")
         _stub("pymatting.util.util", row_sum=eigs_ref.row_sum)
         _stub("pymatting.util.kdtree", knn=lambda data, query, k: eigs_ref.knn_exact(data, query, k))
+        _stub("pymatting.laplacian")
+        _stub("pymatting.laplacian.rw_laplacian", _rw_laplacian=eigs_ref.rw_laplacian_values)
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self  # extract.py:146 on a GPU-less box
     sys.path.insert(0, str(REFERENCE_DIR))

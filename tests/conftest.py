@@ -30,4 +30,7 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     torch.set_grad_enabled(False)
+    # the fp32 oracle runs on the GPU in several tests: keep it true fp32 (no TF32 in matmuls / cuDNN convolutions)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     return torch.device("cuda:0")

@@ -13,7 +13,8 @@ import torch
 from conftest import ROOT, load_pkg
 from oracle import dino_vit, eigs_ref, ref_shim
 
-GOLDEN = sorted((ROOT / "tests" / "golden").glob("*.npz"))
+GOLDEN = sorted((ROOT / "tests" / "golden").glob("lap_*.npz"))
+SEG_GOLDEN = sorted((ROOT / "tests" / "golden").glob("seg_*.npz"))
 torch.set_grad_enabled(False)
 
 
@@ -171,3 +172,68 @@ def test_preprocess_matches_torchvision_transform():
     t = tv.transforms.Compose([tv.transforms.ToTensor(), tv.transforms.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
     want = t(img.numpy())[None, :, :240, :320]
     assert torch.equal(dino_vit.preprocess_u8(img, 16), want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: segmentation workers (extract.py:283-411) and the random-walk colour affinity (extract_utils.py:191-204)
+def load_seg_golden(path):
+    z = np.load(path, allow_pickle=False)
+    return z, ast.literal_eval(str(z["kwargs"]))
+
+
+@pytest.mark.parametrize("path", SEG_GOLDEN, ids=[p.stem for p in SEG_GOLDEN])
+def test_segmentation_oracle_reproduces_reference_golden(path):
+    """oracle/segment_ref.py against the PNGs the reference's own functions wrote (oracle/make_golden.py)."""
+    from oracle import segment_ref
+    z, kw = load_seg_golden(path)
+    P = int(z["patch"])
+    Hp, Wp = int(z["shape"][2]) // P, int(z["shape"][3]) // P
+    single = segment_ref.single_region(z["eigenvectors"], Hp, Wp, float(z["threshold"]))
+    assert np.array_equal(single, z["single"])
+    np.random.seed(1234)                       # same RNG state as the generating call: labels are then identical too
+    multi = segment_ref.multi_region(z["eigenvalues"], z["eigenvectors"], z["feats"], Hp, Wp, **kw)
+    assert np.array_equal(multi, z["multi"])
+    assert segment_ref.same_partition(multi, z["band"])          # and it is the planted partition
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference sources only exist in the dev container")
+def test_segmentation_oracle_matches_live_reference(tmp_path):
+    from PIL import Image
+    from oracle import make_golden, segment_ref
+    ref = ref_shim.load_reference()
+    vals, vecs, feats, band = make_golden.planted_eigs(7, 11, 4, 17)
+    fdir, edir, o1, o2 = (tmp_path / n for n in ("f", "e", "s", "m"))
+    for d in (fdir, edir, o1, o2):
+        d.mkdir()
+    fd = {"k": feats[None], "indices": torch.tensor(0), "file": "x.jpg", "id": "x", "model_name": "dino_vits16",
+          "patch_size": 16, "shape": (1, 3, 7 * 16 + 3, 11 * 16)}
+    torch.save(fd, fdir / "x.pth")
+    torch.save({"eigenvalues": vals, "eigenvectors": vecs}, edir / "x.pth")
+    inp = ref.utils.get_paired_input_files(str(fdir), str(edir))[0]
+    ref._extract_single_region_segmentations(inp, threshold=0.0, output_dir=str(o1))
+    kw = dict(adaptive=True, non_adaptive_num_segments=4, infer_bg_index=True, kmeans_baseline=False, num_eigenvectors=3)
+    np.random.seed(7)
+    ref._extract_multi_region_segmentations(inp, output_dir=str(o2), **kw)
+    assert np.array_equal(np.array(Image.open(o1 / "x.png")), segment_ref.single_region(vecs.numpy(), 7, 11, 0.0))
+    np.random.seed(7)
+    assert np.array_equal(np.array(Image.open(o2 / "x.png")),
+                          segment_ref.multi_region(vals.numpy(), vecs.numpy(), feats.numpy(), 7, 11, **kw))
+    seg = np.array(Image.open(o2 / "x.png"))
+    i1, c1 = segment_ref.get_border_fraction(seg)
+    i2, c2 = ref.utils.get_border_fraction(seg)
+    assert np.array_equal(i1, i2) and np.array_equal(c1, c2)
+
+
+def test_rw_affinity_restatement_properties():
+    """pymatting's _rw_laplacian restated (oracle/eigs_ref.py): 3x3 clamped stencil, duplicates summed by csr_matrix."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (6, 9, 3)) / 255.0
+    vals, ii, jj = eigs_ref.rw_laplacian_values(img, 0.033, 1)
+    assert vals.shape == (6 * 9 * 9,) and ii.dtype == np.int32 and jj.dtype == np.int32
+    # pymatting's loop order: pixel-major, offsets (dy, dx) fastest; first pixel (corner): 4 of its 9 entries are itself
+    assert np.array_equal(ii[:9], np.zeros(9)) and list(jj[:9]) == [0, 0, 1, 0, 0, 1, 9, 9, 10]
+    W = eigs_ref.rw_affinity(img).toarray()
+    assert np.array_equal(W, W.T) and W[0, 0] == 4.0 and W[4, 4] == 2.0 and W[9 + 4, 9 + 4] == 1.0
+    zi, zj = img[2, 3], img[3, 4]
+    assert abs(W[2 * 9 + 3, 3 * 9 + 4] - np.exp(-900 * np.linalg.norm(zi - zj) ** 2)) < 1e-15
+    assert (W > 0).sum(1).max() <= 9

@@ -21,12 +21,19 @@ def test_cuda_path_reproduces_reference_outputs(cuda, path):
     K = int(z["K"])
     lam = float(kw.get("image_color_lambda", 0.0))
     rgb, lr_size = None, None
+    which_color = kw.get("which_color_matrix", "knn")
     if lam > 0:
         lr = z["image_lr"]
         lr_size = (lr.shape[0], lr.shape[1])
-        rgb = torch.from_numpy(lr.reshape(1, -1, 3).astype(np.float32)).to(cuda)
+        if which_color == "rw":     # the uint8 pixels of the low-resolution image (the fixture stores them / 255)
+            u8 = np.rint(lr * 255.0).astype(np.uint8)
+            assert np.array_equal(u8 / 255.0, lr)
+            rgb = torch.from_numpy(u8.reshape(1, -1, 3)).to(cuda)
+        else:
+            rgb = torch.from_numpy(lr.reshape(1, -1, 3).astype(np.float32)).to(cuda)
     ev, vec, info, _ = spectral.laplacian_eigs(feats[None].to(cuda), K, kw.get("normalize", True),
-                                               kw.get("threshold_at_zero", True), kw.get("lapnorm", True), rgb, lr_size, lam)
+                                               kw.get("threshold_at_zero", True), kw.get("lapnorm", True), rgb, lr_size, lam,
+                                               which_color_matrix=which_color)
     torch.cuda.synchronize()
     assert int(info[0, 1]) == 1
     ev, vec = ev[0].cpu().numpy(), vec[0].cpu().numpy()
@@ -48,7 +55,7 @@ def test_knn_counts_match_reference_sparse_matrix(cuda):
     spectral = load_pkg("spectral")
     for path in GOLDEN:
         z, kw = load_golden(path)
-        if not kw.get("image_color_lambda", 0):
+        if not kw.get("image_color_lambda", 0) or kw.get("which_color_matrix", "knn") != "knn":
             continue
         lr = z["image_lr"]
         want = eigs_ref.knn_affinity(lr).toarray()
