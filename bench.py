@@ -263,17 +263,18 @@ def as_shipped_baseline(model_name, size, K, n_images, dev):
     torch.cuda.synchronize()
     t_vit = (time.perf_counter() - t0) / n_images
     tmp = tempfile.mkdtemp(prefix="dss_asshipped_")
-    t0 = time.perf_counter()
     paths = []
+    t_aff = 0.0
     for i, f in enumerate(feats):                                                # extract.py:146-148,191-195
+        t0 = time.perf_counter()
         g = torch.nn.functional.normalize(f[0].to(dev), p=2, dim=-1)
         W = g @ g.T
         W = W * (W > 0)
         W = (W / W.max()).cpu().numpy()
+        t_aff += time.perf_counter() - t0
         paths.append(os.path.join(tmp, f"w{i}.npy"))
-        np.save(paths[-1], W)
-    torch.cuda.synchronize()
-    t_aff = (time.perf_counter() - t0) / n_images
+        np.save(paths[-1], W)                                                    # (hand-over to the worker pool: not timed)
+    t_aff /= n_images
     with CpuPool(model_name, threads_per_worker=1, max_workers=os.cpu_count() or 1, need_vit=False) as pool:
         pool.map(_affinity_eigs_task, [(paths[i % n_images], K) for i in range(pool.workers)])     # warm-up
         reps = max(1, (2 * pool.workers) // n_images)
@@ -288,7 +289,7 @@ def as_shipped_baseline(model_name, size, K, n_images, dev):
     per_image = t_vit + t_aff + t_eig
     return {"value": 1.0 / per_image, "unit": "images/s",
             "what": "reference as shipped: eager fp32 ViT on this GPU (batch 1) + GPU matmul + CPU scipy eigsh pool",
-            "per_image_ms": {"vit_gpu_eager_incl_copies": t_vit * 1e3, "affinity_gpu_plus_w_to_host_and_file": t_aff * 1e3,
+            "per_image_ms": {"vit_gpu_eager_incl_copies": t_vit * 1e3, "affinity_gpu_plus_w_to_host": t_aff * 1e3,
                              "degree_cpu_in_worker": 1e3 * sum(p_[0] for p_ in parts) / len(parts),
                              "eigsh_cpu_in_worker": 1e3 * sum(p_[1] for p_ in parts) / len(parts),
                              "eigs_stage_amortised_over_pool": t_eig * 1e3},
@@ -601,6 +602,19 @@ def run_c2(ctx: Ctx):
                 a = max(a, float(np.abs(v[k] - sgn * vo[k]).max()))
             return r, a
         rel_same = [errs(evecs[i], same[i][3]) for i in range(n)]
+        # images over the tolerance: who is off, the CUDA solver or the reference's float32 ARPACK + LU route? Both are
+        # compared with a float64 dense eigensolve of the same float32 affinity (ground truth), next to the eigen-gaps
+        flagged = sorted(range(n), key=lambda i: -rel_same[i][0])
+        flagged = [i for i in flagged if rel_same[i][0] > 1e-4][:8]
+        over = []
+        if flagged:
+            from oracle import eigs_ref
+            for i in flagged:
+                vals64, vec64 = eigs_ref.eigh_f64(feats[i], K + 1)
+                gaps = [float(min(abs(vals64[k] - vals64[j]) for j in range(K + 1) if j != k)) for k in range(K)]
+                over.append({"image": i, "rel_l2_ours_vs_reference": rel_same[i][0],
+                             "rel_l2_ours_vs_float64": errs(evecs[i], vec64[:K])[0],
+                             "rel_l2_reference_vs_float64": errs(same[i][3], vec64[:K])[0], "min_eigengap": min(gaps)})
         rel_e2e = [errs(evecs[i], parts[i][3])[0] for i in range(n)]
         fb_same = [i for i in range(n) if same[i][1] == "SM-fallback"]
         fb_e2e = [i for i in range(n) if parts[i][2] == "SM-fallback"]
@@ -610,6 +624,7 @@ def run_c2(ctx: Ctx):
             "eigvec_max_abs_err": max(a for _, a in rel_same),
             "eigvec_rel_l2_same_features_median": float(np.median([r for r, _ in rel_same])),
             "images_over_tolerance_same_features": sum(1 for r, _ in rel_same if r > 1e-4),
+            "over_tolerance_detail": over,
             "eigvec_rel_l2_end_to_end_vs_fp32_oracle": max(rel_e2e),
             "eigvec_rel_l2_end_to_end_median": float(np.median(rel_e2e)),
             "reference_singular_lu_fallback": {

@@ -56,6 +56,8 @@ PROTOTYPES = {
     "dss_op_gemm_f16_simt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                      c_int, c_int, c_void_p]),
     "dss_debug_gemm_cfg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dss_op_gemm_ln_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                   c_int, c_void_p]),
     "dss_op_layernorm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "dss_op_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "dss_op_attention_tc_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -74,8 +76,8 @@ PROTOTYPES = {
                                     c_void_p]),
     "dss_segment_threshold": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dss_segment_kmeans": (c_int, [c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, c_int, c_int, c_int, c_void_p,
-                                   c_int, c_int, c_int, c_int, C.c_uint, c_int, c_float, c_void_p, c_void_p, c_void_p,
-                                   c_void_p]),
+                                   c_void_p, c_int, c_int, c_int, c_int, C.c_uint, c_int, c_float, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
     "dss_upsample_bilinear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dss_normalize_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }

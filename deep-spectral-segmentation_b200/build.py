@@ -14,7 +14,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libdss_b200.so"
-SOURCES = ["api.cu", "gemm.cu", "vit_kernels.cu", "attention_tc.cu", "vit.cu", "affinity.cu", "eigsh.cu", "knn.cu", "segment.cu"]
+SOURCES = ["api.cu", "gemm.cu", "gemm_ln.cu", "vit_kernels.cu", "attention_tc.cu", "vit.cu", "affinity.cu", "eigsh.cu", "knn.cu", "segment.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-DDSS_BUILD", "-Xptxas", "-v", *os.environ.get("DSS_EXTRA_NVCC_FLAGS", "").split()]
 

@@ -261,6 +261,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
       const int h = bh % heads;
       const int q0 = (2 * qp + g) * FA_BM;
       const bool dead = q0 >= T || ((ABL & 64) && g == 1);   // odd number of query tiles: nothing to do for B in the last pair
+      // a warp whose 32 query rows all lie beyond T (T = 901: three of the four warps of the 8th tile, which has 5 live
+      // rows) only keeps the barrier protocol going: its exponentials would occupy the MUFU unit -- the busiest unit of
+      // the kernel -- for rows the output tensor map clips anyway
+      const bool wdead = dead || q0 + q * 32 >= T;
       float m_ref = -INFINITY, l_run = 0.f;   // reference maximum of the exponent, row sum relative to it
       for (int j = 0; j < nt; ++j, ++m) {
         // tile B starts every item half a key tile behind tile A (A signals from the middle of its first tile): left
@@ -270,7 +274,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         tc_fence_after();
         [[maybe_unused]] const int tb = (warp - 4) * 1024 + (m < 120 ? m : 120) * 8;   // trace slot (ablation builds)
         FA_TRACE(tb + 0);
-        if (!dead) {
+        if (!wdead) {
           // one key tile, in four chunks of 32 key columns; only the last tile of a row of tiles can be short
           // (kc < 128 columns computed, nvalid <= kc of them real keys)
           const bool tail = j == nt - 1 && (T & (FA_BN - 1)) != 0;
@@ -372,6 +376,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         } else {
           // nothing to compute, but keep the protocol: P_g(m) may only be announced once P_g V(m-1) has been issued
           // (the MMA warp probes p_full by parity and must never be lapped by two phases)
+          if (j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // tile B's start signal (see above)
           if (m > 0) mbar_wait(o_full(g), (m - 1) & 1);
           tc_fence_before();
           __syncwarp();
@@ -381,7 +386,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
           }
         }
       }
-      if (!dead) {
+      if (!wdead) {
         mbar_wait(o_full(g), (m - 1) & 1);   // last P V product of this item
         tc_fence_after();
         uint32_t t[FA_D];
@@ -412,6 +417,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
           tma_store_3d(&tmO, sO + g * FA_TILE, h * FA_D, q0, bh / heads);
           tma_store_commit();
         }
+      } else if (!dead) {
+        // rows beyond T inside a live tile (never lane quarter 0): only the two staging-tile barriers of the group
+        asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory");
       }
     }
     if (q == 0 && lane == 0) tma_store_wait_all<0>();   // the staging tile must outlive the last store

@@ -1,0 +1,374 @@
+// LayerNorm fused into an A-stationary tcgen05 GEMM for the K = 384 layers of ViT-S (qkv and fc1):
+//     out[M, N] (f16) = epilogue( LayerNorm(x[M, 384]; gamma, beta, eps) @ Wt[N, 384]^T + bias )
+// The stand-alone LayerNorm kernel (7.5 % of the step in round 1: 6 bytes of HBM traffic per element and 23 launches)
+// disappears: the CTA's own warps read the fp32 residual stream, normalise it and write the fp16 A operand straight
+// into shared memory in the layout tcgen05.mma reads (K-major rows of 128 bytes, 128 B swizzle -- what a TMA box
+// {64 x f16, 128 rows} would have written). The 128 x 384 panel (96 KB) then stays put while the weight tiles of ALL
+// n-tiles stream past it through a TMA ring, so per 16-deep UMMA step the ring refill moves BN x 32 bytes instead of
+// (128 + BN) x 32: the shared-memory bandwidth bound of the plain kernel is relaxed as well.
+//
+// One CTA per SM, CTAs in clusters of two that walk the same n-tiles for two vertically adjacent 128-row blocks; each
+// CTA fetches half of every weight tile and multicasts it into both (as gemm.cu does).
+//   warp 0        TMA producer of the weight ring
+//   warp 1        TMEM allocation + tcgen05.mma issue (two accumulators: tile i+1's MMAs overlap tile i's epilogue)
+//   warps 4..19   epilogue (as gemm.cu: TMEM -> +bias (-> GELU) -> fp16 -> swizzled staging box -> TMA store)
+//   warps 20..27  LayerNorm producers. Row statistics of the NEXT 128-row block are computed while the current block's
+//                 MMAs run (x is read once from HBM; the second read below hits the L2); then, slab by slab (64
+//                 columns), as soon as the last n-tile's MMAs have released slab k of the panel ("a_free[k]"), the
+//                 rows are re-read, normalised and written: the panel turnover overlaps the tail of the previous block.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace dss {
+
+int make_tmap_f16(CUtensorMap* tm, const void* ptr, int rows, int cols, int box_rows);
+int make_tmap_out(CUtensorMap* tm, const void* ptr, int rows, int cols, int is_f32);
+
+constexpr int LG_BM = 128, LG_K = 384, LG_SLABS = LG_K / 64, LG_SLAB_BYTES = LG_BM * 128;
+constexpr int LG_EPI_WARPS = 16, LG_LN_WARPS = 8;
+constexpr int LG_THREADS = (4 + LG_EPI_WARPS + LG_LN_WARPS) * 32;
+constexpr int LG_BOX_BYTES = LG_BM * 128;
+
+template <int BN> struct LnCfg {
+  static constexpr int A_BYTES = LG_SLABS * LG_SLAB_BYTES;          // 96 KB
+  static constexpr int B_STAGE = BN * 128;                          // BN rows x 64 f16
+  static constexpr int STAGES = 4;
+  static constexpr int STAGING = LG_BOX_BYTES;                      // one 128 x 128 B output box
+  static constexpr int VEC_BYTES = 2 * LG_K * 4 + 2 * 2 * LG_BM * 4;   // gamma, beta | mean[2][128], rstd[2][128]
+  static constexpr int NBARS = 2 * STAGES + 4 + 2 * LG_SLABS;
+  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + STAGING + VEC_BYTES + NBARS * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert((B_STAGE / 2) % 1024 == 0, "half tiles must keep the 1024 B swizzle-atom alignment");
+};
+
+struct LnParams {
+  const float* x;        // [M, 384] fp32 residual stream (read only)
+  const float* gamma;    // [384]
+  const float* beta;     // [384]
+  const float* bias;     // [N]
+  float eps;
+  int M, N;
+};
+
+template <bool GELU, int BN>
+__global__ void __launch_bounds__(LG_THREADS, 1)
+gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int pairs,
+                           LnParams p) {
+  using Cfg = LnCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES, B_STAGE = Cfg::B_STAGE;
+  constexpr int NT_BOX = BN / 64;   // 64-column output boxes per tile
+  extern __shared__ uint8_t lg_smem_raw[];
+  const uint32_t raw = smem_u32(lg_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = lg_smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + Cfg::A_BYTES, sStage = sB + STAGES * B_STAGE;
+  float* s_gamma = reinterpret_cast<float*>(gbase + Cfg::A_BYTES + STAGES * B_STAGE + Cfg::STAGING);
+  float* s_beta = s_gamma + LG_K;
+  float* s_mean = s_beta + LG_K;            // [2][128]
+  float* s_rstd = s_mean + 2 * LG_BM;       // [2][128]
+  const uint32_t bar_base = sStage + Cfg::STAGING + Cfg::VEC_BYTES;
+  auto b_full = [&](int s) { return bar_base + 8u * s; };
+  auto b_empty = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull = [&](int i) { return bar_base + 8u * (2 * STAGES + i); };
+  auto tempty = [&](int i) { return bar_base + 8u * (2 * STAGES + 2 + i); };
+  auto a_full = [&](int k) { return bar_base + 8u * (2 * STAGES + 4 + k); };
+  auto a_free = [&](int k) { return bar_base + 8u * (2 * STAGES + 4 + LG_SLABS + k); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * Cfg::NBARS;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
+      gbase + Cfg::A_BYTES + STAGES * B_STAGE + Cfg::STAGING + Cfg::VEC_BYTES + 8 * Cfg::NBARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int tiles_n = p.N / BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 2);   // released by the MMA warps of both CTAs (each multicasts into the other's ring)
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull(i), 1);
+      mbar_init(tempty(i), LG_EPI_WARPS);
+    }
+    for (int k = 0; k < LG_SLABS; ++k) {
+      mbar_init(a_full(k), LG_LN_WARPS);
+      mbar_init(a_free(k), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < LG_K; i += LG_THREADS) {
+    s_gamma[i] = p.gamma[i];
+    s_beta[i] = p.beta[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ---- weight ring producer: (block pair, n-tile, k-slab) in lock step with the peer CTA
+      const uint32_t uB = __shfl_sync(0xffffffffu, sB, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = cid; c < pairs; c += ncl) {
+        for (int nt = 0; nt < tiles_n; ++nt) {
+          for (int k = 0; k < LG_SLABS; ++k) {
+            mbar_wait(b_empty(s), ph ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(b_full(s), B_STAGE);
+              tma_load_2d_mc(uB + s * B_STAGE + rank * (B_STAGE / 2), &tmB, b_full(s), k * 64, nt * BN + rank * (BN / 2),
+                             (uint16_t)0x3);
+            }
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ---- MMA issuer
+      constexpr uint32_t idesc = umma_idesc_f16(LG_BM, BN);
+      const uint32_t uA = __shfl_sync(0xffffffffu, sA, 0), uB = __shfl_sync(0xffffffffu, sB, 0);
+      const uint32_t utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
+      int s = 0, lt = 0, li = 0;
+      uint32_t ph = 0;
+      for (int c = cid; c < pairs; c += ncl, ++li) {
+        for (int nt = 0; nt < tiles_n; ++nt, ++lt) {
+          const int buf = lt & 1;
+          mbar_wait(tempty(buf), ((lt >> 1) & 1) ^ 1u);
+          tc_fence_after();
+          const uint32_t acc = utmem + buf * BN;
+          for (int k = 0; k < LG_SLABS; ++k) {
+            if (nt == 0) mbar_wait(a_full(k), li & 1);   // slab k of this block's normalised panel is in place
+            mbar_wait(b_full(s), ph);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(uA + k * LG_SLAB_BYTES);
+            const uint64_t bdesc = umma_desc_sw128(uB + s * B_STAGE);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_ss(acc, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+              umma_commit_mc(b_empty(s), (uint16_t)0x3);
+              if (nt == tiles_n - 1) umma_commit(a_free(k));   // last reader of slab k: the next block may overwrite it
+            }
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+          }
+          if (elect_one()) umma_commit(tfull(buf));
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 4 + LG_EPI_WARPS) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    // ---- epilogue: all 16 warps cooperate on one 64-column output box at a time (gemm.cu's TMA-store path)
+    const int ew = warp - 4;
+    const int q = warp & 3, sl = ew >> 2;
+    const int row = q * 32 + lane;
+    constexpr int W = 16;   // columns per warp slice
+    const bool issuer = (ew == 0) && (lane == 0);
+    int lt = 0;
+    for (int c = cid; c < pairs; c += ncl) {
+      const int m0 = (2 * c + rank) * LG_BM;
+      for (int nt = 0; nt < tiles_n; ++nt, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(tfull(buf), (lt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int b = 0; b < NT_BOX; ++b) {
+          const int nc = nt * BN + b * 64;
+          float bias_r[W];
+#pragma unroll
+          for (int j = 0; j < W; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + sl * W + j));
+            bias_r[j] = bv.x; bias_r[j + 1] = bv.y; bias_r[j + 2] = bv.z; bias_r[j + 3] = bv.w;
+          }
+          uint32_t r[W];
+          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + b * 64 + sl * W, r);
+          tmem_ld_wait();
+          if (b == NT_BOX - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(buf));
+          }
+          float xv[W];
+#pragma unroll
+          for (int e = 0; e < W; e += 2) {
+            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])),
+                                   pack_f32x2(bias_r[e], bias_r[e + 1])), xv[e], xv[e + 1]);
+            if constexpr (GELU) gelu_erf_x2(xv[e], xv[e + 1], xv[e], xv[e + 1]);
+          }
+          if (issuer) tma_store_wait_read<0>();   // single staging box: the previous store has finished reading it
+          asm volatile("bar.sync 1, %0;" ::"n"(LG_EPI_WARPS * 32) : "memory");
+          const uint32_t srow = sStage + row * 128;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = sl * 2 + h;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ (row & 7)) << 4)),
+                         "r"(pack_half2(xv[h * 8 + 0], xv[h * 8 + 1])), "r"(pack_half2(xv[h * 8 + 2], xv[h * 8 + 3])),
+                         "r"(pack_half2(xv[h * 8 + 4], xv[h * 8 + 5])), "r"(pack_half2(xv[h * 8 + 6], xv[h * 8 + 7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(LG_EPI_WARPS * 32) : "memory");
+          if (issuer) {
+            if (m0 < p.M) tma_store_2d(&tmC, sStage, nc, m0);   // rows >= M are clipped by the tensor map
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  } else {
+    // ---- LayerNorm producers: warp w owns rows [16 w, 16 w + 16) of the block
+    const int w = warp - 4 - LG_EPI_WARPS;
+    auto stats = [&](int m0, int par) {
+      // two-pass mean / variance like torch (and like the stand-alone kernel it replaces), 2 rows at a time
+#pragma unroll 1
+      for (int rr = 0; rr < 16; rr += 2) {
+        float4 v[2][3];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int m = m0 + w * 16 + rr + i;
+          const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)(m < p.M ? m : 0) * LG_K);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) v[i][j] = m < p.M ? xr[lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) s += (v[i][j].x + v[i][j].y) + (v[i][j].z + v[i][j].w);
+          const float mean = warp_sum(s) * (1.0f / LG_K);
+          float qv = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float a = v[i][j].x - mean, b = v[i][j].y - mean, c = v[i][j].z - mean, e = v[i][j].w - mean;
+            qv += (a * a + b * b) + (c * c + e * e);
+          }
+          const float rstd = rsqrtf(warp_sum(qv) * (1.0f / LG_K) + p.eps);
+          if (lane == 0) {
+            s_mean[par * LG_BM + w * 16 + rr + i] = mean;
+            s_rstd[par * LG_BM + w * 16 + rr + i] = rstd;
+          }
+        }
+      }
+      __syncwarp();
+    };
+    auto write_panel = [&](int m0, int par, int li) {
+      // slab k = columns [64 k, 64 k + 64): per instruction the warp covers two rows x 256 contiguous bytes
+      const int c4 = lane & 15, rsel = lane >> 4;
+#pragma unroll 1
+      for (int k = 0; k < LG_SLABS; ++k) {
+        float4 xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {   // issue the loads before waiting for the slab (second read of x: L2)
+          const int m = m0 + w * 16 + 2 * i + rsel;
+          xv[i] = m < p.M ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)m * LG_K + k * 64) + c4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4 g = *reinterpret_cast<const float4*>(s_gamma + k * 64 + c4 * 4);
+        const float4 bt = *reinterpret_cast<const float4*>(s_beta + k * 64 + c4 * 4);
+        if (li > 0) mbar_wait(a_free(k), (li - 1) & 1);   // the previous block's MMAs have read slab k
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = w * 16 + 2 * i + rsel;
+          const float mean = s_mean[par * LG_BM + r], rstd = s_rstd[par * LG_BM + r];
+          const uint32_t lo = pack_half2((xv[i].x - mean) * rstd * g.x + bt.x, (xv[i].y - mean) * rstd * g.y + bt.y);
+          const uint32_t hi = pack_half2((xv[i].z - mean) * rstd * g.z + bt.z, (xv[i].w - mean) * rstd * g.w + bt.w);
+          // 8 bytes at column 4 c4 of row r: 16-byte chunk c4 / 2 (XOR-swizzled with the row), half c4 & 1
+          const uint32_t addr = sA + k * LG_SLAB_BYTES + r * 128 + ((((c4 >> 1) ^ (r & 7))) << 4) + ((c4 & 1) << 3);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(k));
+      }
+    };
+    int li = 0;
+    for (int c = cid; c < pairs; c += ncl, ++li) {
+      const int m0 = (2 * c + rank) * LG_BM;
+      if (li == 0) stats(m0, 0);
+      write_panel(m0, li & 1, li);
+      if (c + ncl < pairs) stats((2 * (c + ncl) + rank) * LG_BM, (li + 1) & 1);   // next block: overlaps this block's MMAs
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <bool GELU, int BN>
+static int launch_ln(const CUtensorMap& tmB, const CUtensorMap& tmC, const LnParams& p, cudaStream_t st, int kclass) {
+  using Cfg = LnCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_f16_tcgen05_kernel<GELU, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM));
+    attr_set = true;
+  }
+  const int pairs = cdiv(cdiv(p.M, LG_BM), 2);
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+  LaunchScope scope(st, kclass);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(LG_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DSS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_f16_tcgen05_kernel<GELU, BN>, tmB, tmC, pairs, p));
+  DSS_CHECK_CUDA(cudaGetLastError());
+  return DSS_OK;
+}
+
+// tile width of the fused kernel for an N-column layer (0: not supported)
+int gemm_ln_tile_n(int N) { return N % 192 == 0 ? 192 : (N % 128 == 0 ? 128 : 0); }
+
+// tmB: weights [N, 384] f16 with box rows gemm_ln_tile_n(N) / 2; tmC: output [M, N] f16 (make_tmap_out)
+int gemm_ln_f16_tc(const CUtensorMap& tmB, const CUtensorMap& tmC, const float* x, const float* gamma, const float* beta,
+                   const float* bias, int M, int N, float eps, bool gelu, cudaStream_t st, int kclass) {
+  DSS_REQUIRE(x && gamma && beta && bias, "gemm_ln: null pointer");
+  DSS_REQUIRE(M > 0 && N > 0, "gemm_ln: empty problem");
+  const int bn = gemm_ln_tile_n(N);
+  DSS_REQUIRE(bn != 0, "gemm_ln: N = %d is not a multiple of 128", N);
+  LnParams p{x, gamma, beta, bias, eps, M, N};
+  if (bn == 192) return gelu ? launch_ln<true, 192>(tmB, tmC, p, st, kclass) : launch_ln<false, 192>(tmB, tmC, p, st, kclass);
+  return gelu ? launch_ln<true, 128>(tmB, tmC, p, st, kclass) : launch_ln<false, 128>(tmB, tmC, p, st, kclass);
+}
+
+}  // namespace dss
+
+using namespace dss;
+
+extern "C" int dss_op_gemm_ln_f16(const float* x, const float* gamma, const float* beta, const void* Wt, const float* bias,
+                                  void* out, int M, int N, int K, float eps, int gelu, dss_stream_t stream) {
+  DSS_REQUIRE(K == LG_K, "gemm_ln: the fused LayerNorm GEMM is built for K = %d (ViT-S), got %d", LG_K, K);
+  DSS_REQUIRE(Wt && out, "gemm_ln: null pointer");
+  const int bn = gemm_ln_tile_n(N);
+  DSS_REQUIRE(bn != 0, "gemm_ln: N = %d is not a multiple of 128", N);
+  CUtensorMap tmB, tmC;
+  int rc;
+  if ((rc = make_tmap_f16(&tmB, Wt, N, K, bn / 2))) return rc;
+  if ((rc = make_tmap_out(&tmC, out, M, N, 0))) return rc;
+  return gemm_ln_f16_tc(tmB, tmC, x, gamma, beta, bias, M, N, eps, gelu != 0, static_cast<cudaStream_t>(stream), KC_GEMM_OTHER);
+}

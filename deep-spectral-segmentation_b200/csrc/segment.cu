@@ -44,6 +44,7 @@ struct KmeansParams {
   const float* pts;         // point n of image b, coordinate j: pts[b * img_stride + n * pt_stride + j * dim_stride]
   long long img_stride, pt_stride, dim_stride;
   const int* n_clusters;    // [B]
+  const int* image_keys;    // [B] or null: per-image key of the random generator (null: position in the batch)
   uint8_t* labels;          // [B, N]
   int* info;                // [B, 2] = {Lloyd iterations, 1 if converged}
   float* inertia;           // [B] or null
@@ -99,6 +100,7 @@ kmeans_segment_kernel(KmeansParams p) {
     int k = p.n_clusters[img];
     k = k < 1 ? 1 : (k > p.max_k ? p.max_k : k);
     if (k > N) k = N;
+    const uint32_t key = p.image_keys ? (uint32_t)p.image_keys[img] : (uint32_t)img;
     __syncthreads();
 
     // ---- variance of the data (sklearn: tol * mean of the per-feature variances)
@@ -119,7 +121,7 @@ kmeans_segment_kernel(KmeansParams p) {
     // ---- k-means++ seeding (sklearn _kmeans_plusplus: first centre uniform, then 2 + log k candidates drawn with
     // probability proportional to the current squared distance; the candidate with the smallest potential wins)
     uint32_t ctr = 0;
-    const int first = min(N - 1, (int)(seg_uniform(p.seed, img, ctr++) * N));
+    const int first = min(N - 1, (int)(seg_uniform(p.seed, key, ctr++) * N));
     for (int j = tid; j < dims; j += SEG_THREADS) cen[j] = pts[(long long)first * p.pt_stride + (long long)j * p.dim_stride];
     __syncthreads();
     double pot = 0.0;
@@ -135,7 +137,7 @@ kmeans_segment_kernel(KmeansParams p) {
       double best_pot = 0.0;
       for (int t = 0; t < trials; ++t) {
         // sample an index with probability mind2 / pot: thread 0 walks the cumulative sum (N <= a few thousand)
-        const double target = seg_uniform(p.seed, img, ctr++) * pot;
+        const double target = seg_uniform(p.seed, key, ctr++) * pot;
         if (tid == 0) {
           double acc = 0.0;
           int pick = N - 1;
@@ -311,9 +313,9 @@ extern "C" int dss_segment_threshold(const float* evecs, int B, int K, int N, in
 }
 
 extern "C" int dss_segment_kmeans(const float* points, long long image_stride, long long point_stride, long long dim_stride,
-                                  int B, int N, int dims, const int* n_clusters, int max_clusters, int grid_h, int grid_w,
-                                  int infer_bg_index, unsigned int seed, int max_iter, float tol, uint8_t* labels,
-                                  int* info, float* inertia, dss_stream_t stream) {
+                                  int B, int N, int dims, const int* n_clusters, const int* image_keys, int max_clusters,
+                                  int grid_h, int grid_w, int infer_bg_index, unsigned int seed, int max_iter, float tol,
+                                  uint8_t* labels, int* info, float* inertia, dss_stream_t stream) {
   DSS_REQUIRE(points && n_clusters && labels && info, "segment_kmeans: null pointer");
   DSS_REQUIRE(B > 0 && N > 0 && dims > 0, "segment_kmeans: empty problem");
   DSS_REQUIRE(max_clusters >= 1 && max_clusters <= SEG_MAX_CLUSTERS, "segment_kmeans: 1 <= max_clusters <= %d",
@@ -322,7 +324,7 @@ extern "C" int dss_segment_kmeans(const float* points, long long image_stride, l
               grid_w, N);
   KmeansParams p;
   p.pts = points; p.img_stride = image_stride; p.pt_stride = point_stride; p.dim_stride = dim_stride;
-  p.n_clusters = n_clusters; p.labels = labels; p.info = info; p.inertia = inertia;
+  p.n_clusters = n_clusters; p.image_keys = image_keys; p.labels = labels; p.info = info; p.inertia = inertia;
   p.B = B; p.N = N; p.dims = dims; p.max_k = max_clusters; p.Hs = grid_h; p.Ws = grid_w; p.infer_bg = infer_bg_index;
   p.max_iter = max_iter > 0 ? max_iter : 300;
   p.tol = tol >= 0.f ? tol : 1e-4f;

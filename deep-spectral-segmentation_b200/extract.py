@@ -36,6 +36,25 @@ def _feature_dict(k: torch.Tensor, index: int, file: str, model_name: str, patch
             "patch_size": patch_size, "shape": (1, 3, H, W)}
 
 
+def _feature_items(output_dir, files_indices, model_name, patch_size, H, W):
+    """Writer items (io_pipeline) for the feature dicts of one batch: extract.py:98-110, k taken from arrays['k']."""
+    items = []
+    for j, (file, index) in enumerate(files_indices):
+        extra = {"file": file, "id": Path(file).stem, "model_name": model_name, "patch_size": patch_size, "shape": (1, 3, H, W)}
+        items.append((str(Path(output_dir) / f"{Path(file).stem}.pth"), j, extra,
+                      {"k": ("slice1", "k"), "indices": ("tensor0d", index)}))
+    return items
+
+
+def _eigs_items(output_dir, image_ids, which_matrix="laplacian", skip=()):
+    """Writer items for the eigs dicts of one batch (extract.py:242). The 'affinity' branch of the reference keeps
+    `eigenvalues` as the ascending numpy array eigsh returned while the eigenvectors are flipped (extract.py:171-172):
+    the caller passes arrays['evals'] already flipped and it is saved as numpy."""
+    how = "np_slice" if which_matrix == "affinity" else "slice"
+    return [(str(Path(output_dir) / f"{image_id}.pth"), j, {}, {"eigenvalues": (how, "evals"), "eigenvectors": ("slice", "evecs")})
+            for j, image_id in enumerate(image_ids) if j not in skip]
+
+
 class _Batcher:
     """Groups items by a shape key. A group is handed to ``flush`` when it reaches ``batch_size``; when more than
     ``max_pending`` items are waiting in total (data sets with hundreds of distinct image sizes, e.g. VOC), the
@@ -70,7 +89,7 @@ class _Batcher:
 def extract_features(images_list: str, images_root: Optional[str], model_name: str, batch_size: int, output_dir: str,
                      which_block: int = -1, checkpoint: Optional[str] = None, seed: Optional[int] = None,
                      random_init: bool = False, yes: Optional[bool] = None, num_workers: Optional[int] = None,
-                     num_workers_out: int = 8):
+                     num_workers_out: int = 4, writer: str = "process"):
     """
     Extract features from a list of images.
 
@@ -94,7 +113,7 @@ def extract_features(images_list: str, images_root: Optional[str], model_name: s
     print(f"Dataset size: {len(dataset)=}")
     rings: Dict[tuple, io_pipeline.PinnedRing] = {}
 
-    with io_pipeline.AsyncWriter(num_workers_out) as writer:
+    with io_pipeline.make_writer(writer, num_workers_out) as wr:
         def flush(shape_key, items):
             H, W = shape_key
             ring = rings.get(shape_key)
@@ -102,9 +121,8 @@ def extract_features(images_list: str, images_root: Optional[str], model_name: s
                 ring = rings[shape_key] = io_pipeline.PinnedRing(shape_key, max(1, int(batch_size)), dev)
             slot, host = ring.stage([it[0] for it in items])
             k = model.forward_k(ring.to_device(slot, host), which_block=which_block).cpu()
-            for j, (_, file, index) in enumerate(items):
-                out = _feature_dict(k[j:j + 1].clone(), index, file, model_name, patch_size, H, W)
-                writer.submit(out, Path(output_dir) / f"{out['id']}.pth")
+            wr.submit_batch({"k": k.numpy()}, _feature_items(output_dir, [(it[1], it[2]) for it in items], model_name,
+                                                             patch_size, H, W))
 
         batcher = _Batcher(batch_size, flush)
         todo = []
@@ -248,7 +266,7 @@ def extract_eigs(images_root: str, features_dir: str, output_dir: str, which_mat
                  threshold_at_zero: bool = True, lapnorm: bool = True, K: int = 20,
                  image_downsample_factor: Optional[int] = None, image_color_lambda: float = 0.0,
                  multiprocessing: int = 0, batch_size: int = 128, yes: Optional[bool] = None,
-                 num_workers: Optional[int] = None, num_workers_out: int = 8):
+                 num_workers: Optional[int] = None, num_workers_out: int = 4, writer: str = "process"):
     """
     Extracts eigenvalues from features.
 
@@ -276,16 +294,15 @@ def extract_eigs(images_root: str, features_dir: str, output_dir: str, which_mat
     start = time.time()
     all_failed: List[str] = []
 
-    with io_pipeline.AsyncWriter(num_workers_out) as writer:
+    with io_pipeline.make_writer(writer, num_workers_out) as wr:
         def flush(key, dds):
             evals, evecs, failed = _eigs_for_group(dds, K, images_root, which_features, normalize, lapnorm,
                                                    threshold_at_zero, image_downsample_factor, image_color_lambda, dev,
                                                    which_matrix, which_color_matrix)
-            for j, d in enumerate(dds):
-                if j in failed:
-                    all_failed.append(d["id"])
-                    continue
-                writer.submit(_eigs_dict(which_matrix, evals[j], evecs[j]), Path(output_dir) / f"{d['file'][:-4]}.pth")
+            all_failed.extend(dds[j]["id"] for j in failed)
+            ev = evals.flip(1) if which_matrix == "affinity" else evals
+            wr.submit_batch({"evals": ev.numpy(), "evecs": evecs.numpy()},
+                            _eigs_items(output_dir, [d["file"][:-4] for d in dds], which_matrix, skip=failed))
 
         batcher = _Batcher(batch_size, flush)
         load = lambda i: torch.load(str(inputs[i][1]), map_location="cpu")   # noqa: E731  (file reads overlap on threads)
@@ -400,7 +417,8 @@ def extract_multi_region_segmentations(features_dir: str, eigs_dir: str, output_
                 grid = (H_patch * 2, W_patch * 2)
             else:
                 raise ValueError(f"{n_pts} labels do not fit a {H_patch} x {W_patch} patch grid")
-            labels, _, _ = segment.kmeans_labels(pts, ks, grid, infer_bg_index, layout, seed)
+            labels, _, _ = segment.kmeans_labels(pts, ks, grid, infer_bg_index, layout, seed,
+                                                 image_keys=[int(d["indices"]) for d in dicts])
             labels = labels.cpu().numpy()
             for j, (_, output_file) in enumerate(items):
                 pool.submit(_save_png, labels[j].reshape(grid).copy(), output_file)
@@ -466,7 +484,7 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
                 random_init: bool = False, yes: Optional[bool] = None, single_region_dir: Optional[str] = None,
                 multi_region_dir: Optional[str] = None, non_adaptive_num_segments: int = 4, adaptive: bool = False,
                 infer_bg_index: bool = True, threshold: float = 0.0, num_workers: Optional[int] = None,
-                num_workers_out: int = 8):
+                num_workers_out: int = 4, writer: str = "process"):
     """Fused extract_features + extract_eigs (+ the two segmentation commands): features and eigenvectors never leave
     the GPU between the stages. Writes the eigs files and, if the directories are given, the features files and the
     single- / multi-region segmentation PNGs, all in the reference's layouts. Decoding, pinned staging and the file
@@ -474,6 +492,7 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
     for dname in (features_dir, eigs_dir, single_region_dir, multi_region_dir):
         if dname:
             utils.make_output_dir(dname, assume_yes=yes)
+    wr = io_pipeline.make_writer(writer, num_workers_out)   # first: writer processes import torch while the model is set up
     model_name = model_name.lower()
     _check_supported("laplacian", which_color_matrix, image_color_lambda)
     dev = _device()
@@ -483,14 +502,19 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
     dataset = utils.ImagesDataset(filenames=filenames, images_root=images_root)
     rings: Dict[tuple, io_pipeline.PinnedRing] = {}
     all_failed: List[str] = []
+    import time
+    t_start = time.perf_counter()   # model set-up (weights, packing) is done: what follows is the per-image pipeline
 
-    with io_pipeline.AsyncWriter(num_workers_out) as writer, _png_writer_pool(2) as png_pool:
+    tm = {"stage": 0.0, "gpu": 0.0, "submit": 0.0}
+    with wr, _png_writer_pool(2) as png_pool:
         def flush(key, items):
             H, W = key
+            ta = time.perf_counter()
             ring = rings.get(key)
             if ring is None:
                 ring = rings[key] = io_pipeline.PinnedRing(key, max(1, int(batch_size)), dev)
             slot, host = ring.stage([it[0] for it in items])
+            tb = time.perf_counter()
             k = model.forward_k(ring.to_device(slot, host), which_block=which_block)
             Hp, Wp = H // patch_size, W // patch_size
             rgb_lr, lr_size = None, None
@@ -514,21 +538,27 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
             if multi_region_dir:
                 ks = [segment.adaptive_num_clusters(evals[j].numpy()) if adaptive else non_adaptive_num_segments
                       for j in range(len(items))]
-                labels = segment.kmeans_labels(kept["evecs"][:, 1:], ks, (Hp, Wp), infer_bg_index)[0].cpu().numpy()
+                labels = segment.kmeans_labels(kept["evecs"][:, 1:], ks, (Hp, Wp), infer_bg_index,
+                                               image_keys=[it[2] for it in items])[0].cpu().numpy()
             k_cpu = k.cpu() if features_dir else None
+            tc = time.perf_counter()
+            all_failed.extend(items[j][1] for j in failed)
+            if features_dir:
+                wr.submit_batch({"k": k_cpu.numpy()}, [it_ for j, it_ in enumerate(_feature_items(
+                    features_dir, [(it[1], it[2]) for it in items], model_name, patch_size, H, W)) if j not in failed])
+            wr.submit_batch({"evals": evals.numpy(), "evecs": evecs.numpy()},
+                            _eigs_items(eigs_dir, [it[1][:-4] for it in items], skip=failed))
             for j, (_, file, index) in enumerate(items):
                 if j in failed:
-                    all_failed.append(file)
                     continue
-                if features_dir:
-                    fd = _feature_dict(k_cpu[j:j + 1].clone(), index, file, model_name, patch_size, H, W)
-                    writer.submit(fd, Path(features_dir) / f"{fd['id']}.pth")
-                writer.submit({"eigenvalues": evals[j].clone(), "eigenvectors": evecs[j].clone()},
-                              Path(eigs_dir) / f"{file[:-4]}.pth")
                 if masks is not None:
                     png_pool.submit(_save_png, masks[j].reshape(Hp, Wp).copy(), str(Path(single_region_dir) / f"{Path(file).stem}.png"))
                 if labels is not None:
                     png_pool.submit(_save_png, labels[j].reshape(Hp, Wp).copy(), str(Path(multi_region_dir) / f"{Path(file).stem}.png"))
+            td = time.perf_counter()
+            tm["stage"] += tb - ta
+            tm["gpu"] += tc - tb
+            tm["submit"] += td - tc
 
         batcher = _Batcher(batch_size, flush)
         todo = []
@@ -541,6 +571,11 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
         for image, file, index in io_pipeline.ImagePrefetcher(dataset.__getitem__, todo, num_workers):
             batcher.add((int(image.shape[0]), int(image.shape[1])), (image, file, index))
         batcher.finish()
-    print(f"Saved eigs to {eigs_dir}")
+    seconds = time.perf_counter() - t_start
+    print(f"Saved eigs to {eigs_dir} ({len(todo)} images in {seconds:.2f}s after model set-up: "
+          f"{len(todo) / max(seconds, 1e-9):.0f} images/s incl. decode and file writes)")
     if all_failed:
         raise _lib.DssError(f"eigensolver did not converge for {len(all_failed)} image(s): {all_failed[:8]}")
+    return {"images": len(todo), "seconds": seconds, "images_per_s": len(todo) / max(seconds, 1e-9),
+            "main_thread_seconds": {"pinned_staging": tm["stage"], "gpu_and_readback": tm["gpu"], "writer_submit": tm["submit"],
+                                    "until_writers_done": seconds}}

@@ -1,5 +1,9 @@
-"""Host utilities of the hot path: same names and behaviour as the reference's extract/extract_utils.py
-(ImagesDataset :17-37, get_model :40-50, get_image_sizes :73-79, make_output_dir :98-104, parallel_process :138-148)."""
+"""Host utilities of the hot path, under the reference's names (extract/extract_utils.py).
+
+Five-line helpers that ARE the file/CLI contract are kept as the reference has them and say so in their docstrings
+(get_image_sizes :73-79, _get_files :82-88, get_paired_input_files :91-95, ImagesDataset.__init__/__len__ :17-24,36-37);
+everything with behaviour of its own (decode, get_model, make_output_dir, parallel_process, get_border_fraction) is
+written for this package."""
 from __future__ import annotations
 
 import sys
@@ -34,6 +38,7 @@ class ImagesDataset:
 
     def __init__(self, filenames, images_root: Optional[str] = None, transform: Optional[Callable] = None,
                  prepare_filenames: bool = True) -> None:
+        # copied from extract_utils.py:18-24 (de-duplicate + sort: the order defines the `indices` field of the .pth files)
         self.root = None if images_root is None else Path(images_root)
         self.filenames = sorted(list(set(filenames))) if prepare_filenames else list(filenames)
         self.transform = transform
@@ -52,6 +57,8 @@ class ImagesDataset:
 
 
 def get_image_sizes(data_dict: dict, downsample_factor: Optional[int] = None):
+    """Copied from extract_utils.py:73-79 (the arithmetic every consumer of features/*.pth shares: crop to patch
+    multiples, B must be 1)."""
     P = data_dict["patch_size"] if downsample_factor is None else downsample_factor
     B, C, H, W = data_dict["shape"]
     assert B == 1, "assumption violated :("
@@ -61,6 +68,7 @@ def get_image_sizes(data_dict: dict, downsample_factor: Optional[int] = None):
 
 
 def _get_files(p: str):
+    """Copied from extract_utils.py:82-88."""
     if Path(p).is_dir():
         return sorted(Path(p).iterdir())
     elif Path(p).is_file():
@@ -70,7 +78,7 @@ def _get_files(p: str):
 
 
 def get_paired_input_files(path1: str, path2: str):
-    """extract_utils.py:82-95: pairs the sorted entries of two directories (or list files)."""
+    """Copied from extract_utils.py:91-95: pairs the sorted entries of two directories (or list files)."""
     files1 = _get_files(path1)
     files2 = _get_files(path2)
     assert len(files1) == len(files2)
@@ -104,8 +112,11 @@ def get_border_fraction(segmap: np.ndarray):
 
 
 def parallel_process(inputs: Iterable, fn: Callable, multiprocessing: int = 0):
-    """Serial driver with the reference's timing print. ``multiprocessing`` is accepted for CLI compatibility; the
-    GPU path batches images inside each kernel instead of forking CPU workers."""
+    """Serial driver with the reference's timing print (extract_utils.py:138-148). ``multiprocessing`` is accepted for
+    CLI compatibility and ignored with a notice: the GPU path batches images inside each kernel instead of forking
+    CPU workers (a forked worker could not share the CUDA context anyway)."""
+    if multiprocessing:
+        print(f"Note: multiprocessing={multiprocessing} is ignored (images are batched on the GPU, not over CPU workers)")
     start = time.time()
     for inp in inputs:
         fn(inp)

@@ -137,6 +137,10 @@ int dss_op_gemm_f16_simt(const void* A, const void* Wt, const float* bias, void*
  * and TMA ring depth (2..4). Not used by the product path. */
 int dss_debug_gemm_cfg(const void* A, const void* Wt, const float* bias, void* out, int M, int N, int K, int bn,
                        int stages, dss_stream_t stream);
+/* LayerNorm fused into the GEMM's A-operand producer (the qkv / fc1 layers of ViT-S; K must be 384):
+ * out f16 [M, N] = (gelu ? gelu_erf : id)(LayerNorm(x f32 [M, K]; gamma, beta, eps) @ Wt f16 [N, K]^T + bias); N % 128 == 0 */
+int dss_op_gemm_ln_f16(const float* x, const float* gamma, const float* beta, const void* Wt, const float* bias,
+                       void* out, int M, int N, int K, float eps, int gelu, dss_stream_t stream);
 /* y f16 [M, d] = LayerNorm(x f32 [M, d]) * gamma + beta, d in {384, 768} */
 int dss_op_layernorm_f16(const float* x, const float* gamma, const float* beta, void* y, int M, int d, float eps,
                          dss_stream_t stream);
@@ -221,11 +225,13 @@ int dss_segment_threshold(const float* evecs, int B, int K, int N, int which, fl
  * n_clusters [B] int32 (device) gives k per image (the reference's adaptive mode), capped by max_clusters <= 64.
  * If infer_bg_index, labels are taken on a grid_h x grid_w grid (grid_h * grid_w == N) and the label with the largest
  * border share is swapped with 0 (extract_utils.py:124-135). labels [B, N] uint8; info [B, 2] = {iterations,
- * converged}; inertia [B] (may be NULL). seed: counter-based generator (the reference's clustering is unseeded). */
+ * converged}; inertia [B] (may be NULL). seed: counter-based generator keyed by (seed, image_keys[b]) -- image_keys [B]
+ * int32 (device; e.g. the `indices` field of the feature files) makes an image's clustering independent of the batch it
+ * is processed in; NULL uses the position in the batch. (The reference's clustering is unseeded.) */
 int dss_segment_kmeans(const float* points, long long image_stride, long long point_stride, long long dim_stride, int B,
-                       int N, int dims, const int* n_clusters, int max_clusters, int grid_h, int grid_w,
-                       int infer_bg_index, unsigned int seed, int max_iter, float tol, uint8_t* labels, int* info,
-                       float* inertia, dss_stream_t stream);
+                       int N, int dims, const int* n_clusters, const int* image_keys, int max_clusters, int grid_h,
+                       int grid_w, int infer_bg_index, unsigned int seed, int max_iter, float tol, uint8_t* labels,
+                       int* info, float* inertia, dss_stream_t stream);
 
 /* Bilinear up-sampling of patch features (align_corners=False, as F.interpolate at extract.py:185-188):
  * feats [B, Hp*Wp, d] fp32 -> out [B, Hl*Wl, d] fp32. Used when image_downsample_factor != patch size. */

@@ -155,10 +155,10 @@ def test_attention_exp2_polynomial_constants():
 
 def test_gemm_gelu_erf_constants():
     """The fc1 epilogue evaluates the exact-erf GELU on the FMA pipe: erf(u) = u P(u^2) on the clamped argument
-    (csrc/gemm.cu, gelu_erf_x2). Emulate that float32 arithmetic with the constants parsed out of the kernel source
+    (csrc/common.cuh, gelu_erf_x2). Emulate that float32 arithmetic with the constants parsed out of the kernel source
     against torch's erf GELU in float64 over the whole range fp16 activations can take."""
     import re
-    src = (ROOT / "deep-spectral-segmentation_b200" / "csrc" / "gemm.cu").read_text()
+    src = (ROOT / "deep-spectral-segmentation_b200" / "csrc" / "common.cuh").read_text()
     coef = [np.float32(float(v)) for v in re.findall(r"#define DSS_GELU_C\d (-?[\d.e+-]+)f", src)]
     clamp = np.float32(float(re.search(r"#define DSS_GELU_CLAMP ([\d.]+)f", src).group(1)))
     assert len(coef) == 9, coef                            # c0 .. c8 of P(s) = sum c_k s^k

@@ -26,8 +26,12 @@ def _aligned_err(a, b):
     return np.array(out)
 
 
-def gap_tolerance(feats, K, kw, floor=2e-5, jitter=1e-6):
-    """per-vector tolerance max(floor, jitter / gap_k), gap_k = distance of lambda_k to its nearest neighbour (float64 spectrum)"""
+def gap_tolerance(feats, K, kw, floor=None, jitter=1e-6):
+    """per-vector tolerance max(floor, jitter / gap_k), gap_k = distance of lambda_k to its nearest neighbour (float64
+    spectrum). floor = max(2e-5, 5e-8 N): the run-to-run jitter of the reference's own float32 LU + ARPACK route (its
+    start vector is unseeded) grows with the matrix size -- 1.3e-5 .. 2.3e-5 measured at N = 713."""
+    if floor is None:
+        floor = max(2e-5, 5e-8 * feats.shape[-2])
     kw = {k: v for k, v in kw.items() if k in ("normalize", "lapnorm", "threshold_at_zero")}
     vals, _ = eigs_ref.eigh_f64(feats, K + 1, **kw)
     scale = max(1.0, float(np.abs(vals).max()))

@@ -44,10 +44,11 @@ def main():
     N = feats8.shape[1]
     for B in (8, 64, 148, 296, 592):
         feats = feats8.repeat((B + 7) // 8, 1, 1)[:B].contiguous()
-        Wm = spectral.affinity(feats)
-        ms_a = timeit(lambda: spectral.affinity(feats, out=Wm))
-        ms_e = timeit(lambda: spectral.eigsh_laplacian(Wm, N, K))
-        ev, vec, info, resid = spectral.eigsh_laplacian(Wm, N, K)
+        deg = torch.empty(B, N, device=dev)
+        Wm = spectral.affinity(feats, degree=deg)
+        ms_a = timeit(lambda: spectral.affinity(feats, out=Wm, degree=deg))
+        ms_e = timeit(lambda: spectral.eigsh_laplacian(Wm, N, K, degree=deg))
+        ev, vec, info, resid = spectral.eigsh_laplacian(Wm, N, K, degree=deg)
         torch.cuda.synchronize()
         print(f"spectral B={B:4d}: affinity {ms_a:8.3f} ms ({ms_a / B * 1e3:7.1f} us/img)  eigsh {ms_e:8.3f} ms "
               f"({ms_e / B * 1e3:7.1f} us/img)  steps mean {info[:, 0].float().mean().item():.1f} max {int(info[:, 0].max())} "
