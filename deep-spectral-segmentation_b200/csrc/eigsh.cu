@@ -25,8 +25,8 @@ constexpr int EIG_THREADS = 512;
 constexpr int EIG_WARPS = EIG_THREADS / 32;
 constexpr int EIG_MAX_K = 64;
 
-constexpr int EIG_STRIP_CH = 8;                    // float4 column chunks per lane and strip
-constexpr int EIG_STRIP = 32 * 4 * EIG_STRIP_CH;   // 1024 columns per strip
+constexpr int EIG_STRIP_CH = 4;                    // float4 column chunks per lane and strip
+constexpr int EIG_STRIP = 32 * 4 * EIG_STRIP_CH;   // 512 columns per strip
 
 struct EigParams {
   const float* W;     // [B, N, ldw]
@@ -220,52 +220,67 @@ lanczos_laplacian_kernel(EigParams p) {
 #pragma unroll
           for (int k = 0; k < EIG_STRIP_CH; ++k) colacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
           const float4* x4 = reinterpret_cast<const float4*>(xs);
+          const float4* W4 = reinterpret_cast<const float4*>(W);
           // R consecutive rows per warp and pass (r % R == 0, so their diagonal elements share one 4-column chunk)
           for (int r = warp * R; r < N && r < s1; r += EIG_WARPS * R) {
+            // 32-bit chunk offsets from the image's base (N * ldw < 2^31): one IMAD.WIDE per load instead of a 64-bit
+            // row pointer that the 64-register budget forces the compiler to rebuild in every block
             const float4* rowp[R];
             float xr[R], acc[R];
 #pragma unroll
             for (int q = 0; q < R; ++q) {
               const bool ok = r + q < N;
-              rowp[q] = reinterpret_cast<const float4*>(W + (size_t)(ok ? r + q : N - 1) * ldw);
+              rowp[q] = W4 + (((ok ? r + q : N - 1) * ldw) >> 2);
+              // opaque to the optimiser: without this the row pointer is re-derived from (image, row, ldw) inside every
+              // one of the unrolled blocks below (~25 integer instructions per pair of loads)
+              asm volatile("" : "+l"(rowp[q]));
               xr[q] = ok ? xs[r + q] : 0.f;
               acc[q] = 0.f;
             }
             const int chd = r >> 2;                          // chunk that holds the diagonal elements of these rows
+            // warp-uniform range of k blocks (32 chunks each) that intersect columns [max(r, s0), s1): the blocks left
+            // of the diagonal are skipped as a whole, and the per-element masks of the diagonal chunk are only evaluated
+            // in the one block that contains it (round 2, first version: ncu showed 1.2 G warp instructions per launch,
+            // 14 % of them FFMA -- the predicated mask / address arithmetic of all eight blocks was issued for every row)
+            const int cb = s0 >> 2, nch = s1 >> 2;
+            const int k_first = chd > cb ? (chd - cb) >> 5 : 0;
+            const int k_end = ((s1 - s0) + 127) >> 7;
 #pragma unroll
             for (int k = 0; k < EIG_STRIP_CH; ++k) {
-              const int ch = (s0 >> 2) + lane + 32 * k;      // this lane's k-th chunk of the strip: columns 4 ch .. 4 ch + 3
-              if (4 * ch < s1 && ch >= chd) {
+              if (k < k_first || k >= k_end) continue;       // (uniform)
+              const int ch = cb + lane + 32 * k;             // this lane's k-th chunk of the strip: columns 4 ch .. 4 ch + 3
+              if (ch >= chd && ch < nch) {
                 const float4 x = x4[ch];
                 float4 u[R];
 #pragma unroll
                 for (int q = 0; q < R; ++q) u[q] = __ldg(rowp[q] + ch);
-                if (ch == chd) {                             // diagonal chunk: drop the elements left of the diagonal
+                if (k == k_first) {                          // (uniform) the block that holds the diagonal chunk
+                  if (ch == chd) {
+                    // row part: drop the elements left of the diagonal; column part: drop the diagonal as well
+                    float4 c[R];
 #pragma unroll
-                  for (int q = 0; q < R; ++q) {
-                    const int dq = (r + q) & 3;
-                    if (dq > 0) u[q].x = 0.f;
-                    if (dq > 1) u[q].y = 0.f;
-                    if (dq > 2) u[q].z = 0.f;
+                    for (int q = 0; q < R; ++q) {
+                      const int dq = (r + q) & 3;
+                      if (dq > 0) u[q].x = 0.f;
+                      if (dq > 1) u[q].y = 0.f;
+                      if (dq > 2) u[q].z = 0.f;
+                      c[q] = u[q];
+                      if (dq == 0) c[q].x = 0.f;
+                      if (dq == 1) c[q].y = 0.f;
+                      if (dq == 2) c[q].z = 0.f;
+                      if (dq == 3) c[q].w = 0.f;
+                      acc[q] = fmaf(u[q].x, x.x, acc[q]); acc[q] = fmaf(u[q].y, x.y, acc[q]);
+                      acc[q] = fmaf(u[q].z, x.z, acc[q]); acc[q] = fmaf(u[q].w, x.w, acc[q]);
+                      colacc[k].x = fmaf(c[q].x, xr[q], colacc[k].x); colacc[k].y = fmaf(c[q].y, xr[q], colacc[k].y);
+                      colacc[k].z = fmaf(c[q].z, xr[q], colacc[k].z); colacc[k].w = fmaf(c[q].w, xr[q], colacc[k].w);
+                    }
+                    continue;
                   }
                 }
 #pragma unroll
                 for (int q = 0; q < R; ++q) {
                   acc[q] = fmaf(u[q].x, x.x, acc[q]); acc[q] = fmaf(u[q].y, x.y, acc[q]);
                   acc[q] = fmaf(u[q].z, x.z, acc[q]); acc[q] = fmaf(u[q].w, x.w, acc[q]);
-                }
-                if (ch == chd) {                             // the diagonal itself belongs to the row part only
-#pragma unroll
-                  for (int q = 0; q < R; ++q) {
-                    const int dq = (r + q) & 3;
-                    if (dq == 0) u[q].x = 0.f;
-                    if (dq == 1) u[q].y = 0.f;
-                    if (dq == 2) u[q].z = 0.f;
-                    if (dq == 3) u[q].w = 0.f;
-                  }
-                }
-#pragma unroll
-                for (int q = 0; q < R; ++q) {
                   colacc[k].x = fmaf(u[q].x, xr[q], colacc[k].x); colacc[k].y = fmaf(u[q].y, xr[q], colacc[k].y);
                   colacc[k].z = fmaf(u[q].z, xr[q], colacc[k].z); colacc[k].w = fmaf(u[q].w, xr[q], colacc[k].w);
                 }

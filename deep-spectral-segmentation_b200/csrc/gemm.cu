@@ -43,8 +43,8 @@ __host__ __device__ constexpr bool epi_uses_tma_store(int epi) {
 constexpr int default_stages(int bn, bool tma) { return tma ? (bn == 128 ? 3 : 4) : 2; }
 // Shared-memory bandwidth is what bounds the kernel: wide tiles and a deep ring are what matter.
 // CG = 1: one CTA per output tile, the pair shares the weight tile by TMA multicast (each CTA still holds all of it).
-// CG = 2 (EXPERIMENTAL, off unless DSS_GEMM_2CTA=1, not yet validated on hardware): tcgen05.mma.cta_group::2, each CTA
-// holds only ITS half of the weight tile, which halves the B operand traffic per FLOP; the smaller stages buy a deeper ring.
+// CG = 2: tcgen05.mma.cta_group::2, each CTA holds only ITS half of the weight tile, which halves the B operand traffic
+// per FLOP; the smaller stages buy a deeper ring. Used for the long-K residual GEMM (fc2), see launch_tc.
 template <int BN, bool TMA_OUT, int ST = default_stages(BN, TMA_OUT), int CG = 1> struct TileCfg {
   static constexpr int KS = slabs_per_stage(BN);
   static constexpr int A_TILE_BYTES = KS * A_ATOM_BYTES;
@@ -333,6 +333,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t stage_u32 = base + STAGES * STAGE_BYTES;
       int lt = 0, cc = 0;
       [[maybe_unused]] float aff_rowsum = 0.f;       // affinity: this thread's row sum over the tile's columns
+      [[maybe_unused]] float aff_mx = 1.f, aff_unscale = 1.f;
       for (int t = cid; t < total_items; t += ncl, ++lt) {
         const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank, p.tri);
         const int buf = lt & 1;
@@ -373,14 +374,17 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             // W[z, m, n] = relu(acc) / max (+ lambda * counts); columns >= M (row-pitch padding) are zeros; rows >= M
             // are clipped by the per-image (3D) tensor map
             const int m = tc.m0 + row, n = nc + sl * W;
-            const float mx = __uint_as_float(__ldg(p.img_max + tc.z));
-            // un-normalised features were pre-scaled by pre = 2^-ceil(log2 max|f|) (affinity.cu): the scale cancels in
-            // W / max(W); when the division is skipped (which_matrix = 'affinity' / 'affinity_svd') it is undone here
-            float unscale = 1.0f;
-            if ((p.threshold & 2) && p.img_absmax != nullptr) {
-              const float am = __uint_as_float(__ldg(p.img_absmax + tc.z));
-              if (am > 0.f) unscale = exp2f(2.0f * ceilf(log2f(am)));
+            if (b == 0) {   // per-tile constants (L2 round trips: not once per box)
+              aff_mx = __uint_as_float(__ldg(p.img_max + tc.z));
+              // un-normalised features were pre-scaled by pre = 2^-ceil(log2 max|f|) (affinity.cu): the scale cancels
+              // in W / max(W); when the division is skipped (which_matrix = 'affinity' / 'affinity_svd') it is undone
+              aff_unscale = 1.0f;
+              if ((p.threshold & 2) && p.img_absmax != nullptr) {
+                const float am = __uint_as_float(__ldg(p.img_absmax + tc.z));
+                if (am > 0.f) aff_unscale = exp2f(2.0f * ceilf(log2f(am)));
+              }
             }
+            const float mx = aff_mx, unscale = aff_unscale;
             const uint8_t* cnt = (p.counts && m < M) ? p.counts + ((long long)tc.z * M + m) * M + n : nullptr;
 #pragma unroll
             for (int e = 0; e < W; ++e) {
@@ -753,8 +757,13 @@ static int launch_tc_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 template <int EPI>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, int M, int N, int K,
                      const EpiParams& p, cudaStream_t st, int kclass, int bn, int batch = 1) {
-  // EXPERIMENTAL CTA-pair MMA (tcgen05.mma.cta_group::2), opt-in for tuning: DSS_GEMM_2CTA=1. Not the product path.
-  static const bool two_cta = [] { const char* e = getenv("DSS_GEMM_2CTA"); return e && atoi(e) != 0; }();
+  // CTA-pair MMA (tcgen05.mma.cta_group::2: each CTA holds only its half of the weight tile). Validated on hardware in
+  // round 2 (tests/test_ops_gpu.py under DSS_GEMM_2CTA=1); measured on the 296-image step against the multicast form:
+  // fc2 (K = 1536) 1028 vs 931 TFLOP/s, but qkv / fc1 / proj (K = 384) 844 / 720 / 411 vs 1019 / 760 / 439 -- the
+  // pair's shared accumulator-drain handshake costs more than the halved operand traffic saves when a tile has only
+  // six K slabs. Hence: on for the long-K residual GEMM, off elsewhere; DSS_GEMM_2CTA = 0 / 1 forces it.
+  static const int two_cta_env = [] { const char* e = getenv("DSS_GEMM_2CTA"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+  const bool two_cta = two_cta_env >= 0 ? two_cta_env == 1 : (EPI == DSS_EPI_BIAS_RESID_F32 && K >= 1024);
   if constexpr (epi_uses_tma_store(EPI) && EPI != EPI_AFFINITY_F32) {
     if (two_cta) {
       constexpr int D = 0;   // stage count is derived from the shared-memory budget for CG = 2

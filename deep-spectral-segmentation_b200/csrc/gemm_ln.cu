@@ -34,10 +34,12 @@ template <int BN> struct LnCfg {
   static constexpr int A_BYTES = LG_SLABS * LG_SLAB_BYTES;          // 96 KB
   static constexpr int B_STAGE = BN * 128;                          // BN rows x 64 f16
   static constexpr int STAGES = 4;
-  static constexpr int STAGING = LG_BOX_BYTES;                      // one 128 x 128 B output box
-  static constexpr int VEC_BYTES = 2 * LG_K * 4 + 2 * 2 * LG_BM * 4;   // gamma, beta | mean[2][128], rstd[2][128]
+  static constexpr int STAGING = 2 * LG_BOX_BYTES;                  // two 128 x 128 B output boxes (double buffered: with a
+                                                                    // single box every store serialised the 16 epilogue
+                                                                    // warps behind the TMA engine's read of the box)
+  static constexpr int VEC_BYTES = 2 * 2 * LG_BM * 4;               // mean[2][128], rstd[2][128]
   static constexpr int NBARS = 2 * STAGES + 4 + 2 * LG_SLABS;
-  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + STAGING + VEC_BYTES + NBARS * 8 + 16 + 1024;
+  static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + STAGING + VEC_BYTES + NBARS * 8 + 16;
   static constexpr int TMEM_COLS = 512;
   static_assert(SMEM <= 232448, "shared memory budget");
   static_assert((B_STAGE / 2) % 1024 == 0, "half tiles must keep the 1024 B swizzle-atom alignment");
@@ -59,15 +61,13 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
   using Cfg = LnCfg<BN>;
   constexpr int STAGES = Cfg::STAGES, B_STAGE = Cfg::B_STAGE;
   constexpr int NT_BOX = BN / 64;   // 64-column output boxes per tile
-  extern __shared__ uint8_t lg_smem_raw[];
-  const uint32_t raw = smem_u32(lg_smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* gbase = lg_smem_raw + (base - raw);
+  extern __shared__ __align__(1024) uint8_t lg_smem_raw[];
+  const uint32_t base = smem_u32(lg_smem_raw);
+  if ((base & 1023u) != 0) __trap();   // the 128 B swizzle pattern is a function of address bits [7,10)
+  uint8_t* gbase = lg_smem_raw;
   const uint32_t sA = base, sB = base + Cfg::A_BYTES, sStage = sB + STAGES * B_STAGE;
-  float* s_gamma = reinterpret_cast<float*>(gbase + Cfg::A_BYTES + STAGES * B_STAGE + Cfg::STAGING);
-  float* s_beta = s_gamma + LG_K;
-  float* s_mean = s_beta + LG_K;            // [2][128]
-  float* s_rstd = s_mean + 2 * LG_BM;       // [2][128]
+  float* s_mean = reinterpret_cast<float*>(gbase + Cfg::A_BYTES + STAGES * B_STAGE + Cfg::STAGING);   // [2][128]
+  float* s_rstd = s_mean + 2 * LG_BM;                                                                  // [2][128]
   const uint32_t bar_base = sStage + Cfg::STAGING + Cfg::VEC_BYTES;
   auto b_full = [&](int s) { return bar_base + 8u * s; };
   auto b_empty = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -104,10 +104,6 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
   if (warp == 1) {
     tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
     tmem_relinquish();
-  }
-  for (int i = threadIdx.x; i < LG_K; i += LG_THREADS) {
-    s_gamma[i] = p.gamma[i];
-    s_beta[i] = p.beta[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -178,7 +174,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     const int row = q * 32 + lane;
     constexpr int W = 16;   // columns per warp slice
     const bool issuer = (ew == 0) && (lane == 0);
-    int lt = 0;
+    int lt = 0, cc = 0;
     for (int c = cid; c < pairs; c += ncl) {
       const int m0 = (2 * c + rank) * LG_BM;
       for (int nt = 0; nt < tiles_n; ++nt, ++lt) {
@@ -186,7 +182,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         mbar_wait(tfull(buf), (lt >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int b = 0; b < NT_BOX; ++b) {
+        for (int b = 0; b < NT_BOX; ++b, ++cc) {
           const int nc = nt * BN + b * 64;
           float bias_r[W];
 #pragma unroll
@@ -209,9 +205,10 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
                                    pack_f32x2(bias_r[e], bias_r[e + 1])), xv[e], xv[e + 1]);
             if constexpr (GELU) gelu_erf_x2(xv[e], xv[e + 1], xv[e], xv[e + 1]);
           }
-          if (issuer) tma_store_wait_read<0>();   // single staging box: the previous store has finished reading it
+          if (issuer) tma_store_wait_read<1>();   // the store issued two boxes ago has finished reading this buffer
           asm volatile("bar.sync 1, %0;" ::"n"(LG_EPI_WARPS * 32) : "memory");
-          const uint32_t srow = sStage + row * 128;
+          const uint32_t sbuf = sStage + (cc & 1) * LG_BOX_BYTES;
+          const uint32_t srow = sbuf + row * 128;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int j = sl * 2 + h;
@@ -223,7 +220,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, %0;" ::"n"(LG_EPI_WARPS * 32) : "memory");
           if (issuer) {
-            if (m0 < p.M) tma_store_2d(&tmC, sStage, nc, m0);   // rows >= M are clipped by the tensor map
+            if (m0 < p.M) tma_store_2d(&tmC, sbuf, nc, m0);   // rows >= M are clipped by the tensor map
             tma_store_commit();
           }
         }
@@ -278,8 +275,8 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
           xv[i] = m < p.M ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)m * LG_K + k * 64) + c4)
                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const float4 g = *reinterpret_cast<const float4*>(s_gamma + k * 64 + c4 * 4);
-        const float4 bt = *reinterpret_cast<const float4*>(s_beta + k * 64 + c4 * 4);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + k * 64 + c4 * 4));   // 3 KB, L1 resident
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + k * 64 + c4 * 4));
         if (li > 0) mbar_wait(a_free(k), (li - 1) & 1);   // the previous block's MMAs have read slab k
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

@@ -9,37 +9,56 @@ namespace dss {
 // im2col: images_u8 [B,H,W,3] -> patches f16 [B*Np, 3*P*P]; column = c*P*P + py*P + px (the flattening of the
 // Conv2d weight [d,3,P,P]); value = ((u8/255) - mean_c)/std_c  (ToTensor + Normalize, extract_utils.py:53-59).
 // The crop to patch multiples (extract.py:82-88) is implicit: only pixels of whole patches are read.
-// One thread writes 8 consecutive px of one (patch, channel, py) = one 16 B store.
 __constant__ float c_mean[3] = {0.485f, 0.456f, 0.406f};
 __constant__ float c_std[3] = {0.229f, 0.224f, 0.225f};
 
+// One thread = 8 consecutive pixels of one patch row, ALL three channels: it reads the 24 interleaved RGB bytes once
+// (32-bit loads when the address allows; consecutive threads read consecutive 24-byte spans, so a warp covers one
+// contiguous stretch of the image row) and writes three 16-byte stores, one per channel plane of the patch.
+// (Round 1 used one thread per channel with byte loads at stride 3: every input byte was fetched three times; 0.19 of
+// the HBM roofline.)
 __global__ void im2col_f16_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, int B, int H, int W, int P,
                                   int Hp, int Wp) {
   const int groups_per_row = P / 8;                       // 8-px groups per patch row
-  const int per_patch = 3 * P * groups_per_row;           // groups per patch
+  const int per_patch = P * groups_per_row;               // (py, group) pairs per patch
   const long long total = (long long)B * Hp * Wp * per_patch;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int g = (int)(gid % per_patch);
-  const long long patch = gid / per_patch;
-  const int px0 = (g % groups_per_row) * 8;
-  const int py = (g / groups_per_row) % P;
-  const int c = g / (groups_per_row * P);
-  const int pw = (int)(patch % Wp);
-  const int ph = (int)((patch / Wp) % Hp);
-  const int b = (int)(patch / ((long long)Wp * Hp));
-  const uint8_t* src = img + (((long long)b * H + (ph * P + py)) * W + (pw * P + px0)) * 3 + c;
-  const float mean = c_mean[c], sd = c_std[c];
-  float v[8];
+  // consecutive threads walk along an image row: (b, patch row ph, py, patch column pw, group)
+  const int g = (int)(gid % groups_per_row);
+  const int pw = (int)((gid / groups_per_row) % Wp);
+  const int py = (int)((gid / ((long long)groups_per_row * Wp)) % P);
+  const int ph = (int)((gid / ((long long)groups_per_row * Wp * P)) % Hp);
+  const int b = (int)(gid / ((long long)groups_per_row * Wp * P * Hp));
+  const int px0 = g * 8;
+  const uint8_t* src = img + (((long long)b * H + (ph * P + py)) * W + (pw * P + px0)) * 3;
+  uint8_t raw[24];
+  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
 #pragma unroll
-  for (int t = 0; t < 8; ++t) v[t] = (static_cast<float>(src[t * 3]) / 255.0f - mean) / sd;
-  uint4 q;
-  q.x = pack_half2(v[0], v[1]);
-  q.y = pack_half2(v[2], v[3]);
-  q.z = pack_half2(v[4], v[5]);
-  q.w = pack_half2(v[6], v[7]);
-  __half* dst = out + patch * (3LL * P * P) + (c * P + py) * P + px0;
-  *reinterpret_cast<uint4*>(dst) = q;
+    for (int i = 0; i < 6; ++i) {
+      const uint32_t w = __ldg(s4 + i);
+      raw[4 * i] = w & 0xff; raw[4 * i + 1] = (w >> 8) & 0xff; raw[4 * i + 2] = (w >> 16) & 0xff; raw[4 * i + 3] = w >> 24;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) raw[i] = __ldg(src + i);
+  }
+  const long long patch = ((long long)b * Hp + ph) * Wp + pw;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float mean = c_mean[c], sd = c_std[c];
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = (static_cast<float>(raw[t * 3 + c]) / 255.0f - mean) / sd;
+    uint4 q;
+    q.x = pack_half2(v[0], v[1]);
+    q.y = pack_half2(v[2], v[3]);
+    q.z = pack_half2(v[4], v[5]);
+    q.w = pack_half2(v[6], v[7]);
+    __half* dst = out + patch * (3LL * P * P) + (c * P + py) * P + px0;
+    *reinterpret_cast<uint4*>(dst) = q;
+  }
 }
 
 // x[b, 0, :] = cls + pos[0, :]
@@ -272,7 +291,7 @@ int launch_im2col(const uint8_t* img, void* patches, int B, int H, int W, int P,
   DSS_REQUIRE(P % 8 == 0 && P > 0, "im2col: patch must be a multiple of 8 (got %d)", P);
   const int Hp = H / P, Wp = W / P;
   DSS_REQUIRE(B > 0 && Hp > 0 && Wp > 0, "im2col: image %dx%d smaller than one patch", H, W);
-  const long long total = (long long)B * Hp * Wp * 3 * P * (P / 8);
+  const long long total = (long long)B * Hp * Wp * P * (P / 8);
   const int threads = 256;
   LaunchScope scope(st, KC_IM2COL);
   im2col_f16_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(

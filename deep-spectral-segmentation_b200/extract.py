@@ -505,9 +505,48 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
     import time
     t_start = time.perf_counter()   # model set-up (weights, packing) is done: what follows is the per-image pipeline
 
-    tm = {"stage": 0.0, "gpu": 0.0, "submit": 0.0}
+    tm = {"stage": 0.0, "launch": 0.0, "wait_gpu": 0.0, "submit": 0.0}
+    in_flight: List[dict] = []       # batches whose kernels / read-back copies are still running (software pipeline)
     with wr, _png_writer_pool(2) as png_pool:
+        def finish(h):
+            """Second half of a batch: wait for its read-back, retry stragglers, hand everything to the writers."""
+            ta = time.perf_counter()
+            h["event"].synchronize()
+            tb = time.perf_counter()
+            items, H, W, Hp, Wp = h["items"], h["H"], h["W"], h["Hp"], h["Wp"]
+            evals, evecs, info = h["evals"], h["evecs"], h["info"]
+            n_img = len(items)
+            bad = [i for i in range(n_img) if int(info[i, 1]) == 0
+                   or not bool(torch.isfinite(evecs[i]).all() and torch.isfinite(evals[i]).all())]
+            failed = []
+            if bad:   # rare: largest possible Krylov space for the images that did not reach the tolerance
+                ev2, vec2, info2 = (t.cpu() for t in h["solve"](bad, max(Hp * Wp - 1, 1)))
+                for j, i in enumerate(bad):
+                    if int(info2[j, 1]) == 1 and bool(torch.isfinite(vec2[j]).all()):
+                        evals[i], evecs[i] = ev2[j], vec2[j]
+                    else:
+                        failed.append(i)
+            all_failed.extend(items[j][1] for j in failed)
+            if features_dir:
+                wr.submit_batch({"k": h["k"].numpy()}, [it_ for j, it_ in enumerate(_feature_items(
+                    features_dir, [(it[1], it[2]) for it in items], model_name, patch_size, H, W)) if j not in failed])
+            wr.submit_batch({"evals": evals.numpy(), "evecs": evecs.numpy()},
+                            _eigs_items(eigs_dir, [it[1][:-4] for it in items], skip=failed))
+            for j, (_, file, index) in enumerate(items):
+                if j in failed:
+                    continue
+                if h["masks"] is not None:
+                    png_pool.submit(_save_png, h["masks"][j].numpy().reshape(Hp, Wp).copy(),
+                                    str(Path(single_region_dir) / f"{Path(file).stem}.png"))
+                if h["labels"] is not None:
+                    png_pool.submit(_save_png, h["labels"][j].numpy().reshape(Hp, Wp).copy(),
+                                    str(Path(multi_region_dir) / f"{Path(file).stem}.png"))
+            tm["wait_gpu"] += tb - ta
+            tm["submit"] += time.perf_counter() - tb
+
         def flush(key, items):
+            """First half of a batch: stage, copy, enqueue every kernel and the read-back copies; then finish the
+            PREVIOUS batch while this one runs."""
             H, W = key
             ta = time.perf_counter()
             ring = rings.get(key)
@@ -521,44 +560,42 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
             if image_color_lambda > 0:
                 rgb_lr = _color_inputs(images_root, [it[1][:-4] for it in items], Wp, Hp, which_color_matrix, dev)
                 lr_size = (Hp, Wp)
-            kept = {}
 
             def solve(sel, max_steps):
                 f = k if sel is None else k[sel]
                 rgb = rgb_lr if (sel is None or rgb_lr is None) else rgb_lr[sel]
-                out = spectral.laplacian_eigs(f, K, normalize, threshold_at_zero, lapnorm, rgb, lr_size, image_color_lambda,
-                                              max_steps=max_steps, which_color_matrix=which_color_matrix)
-                if sel is None:
-                    kept["evecs"], kept["evals"] = out[1], out[0]
-                return out[:3]
-            evals, evecs, info, failed = _solve_with_retry(solve, len(items), Hp * Wp)
-            masks = labels = None
+                return spectral.laplacian_eigs(f, K, normalize, threshold_at_zero, lapnorm, rgb, lr_size, image_color_lambda,
+                                               max_steps=max_steps, which_color_matrix=which_color_matrix)[:3]
+            evals_d, evecs_d, info_d = solve(None, 0)
+            masks_d = labels_d = None
             if single_region_dir:
-                masks = segment.threshold_masks(kept["evecs"], threshold, which=1).cpu().numpy()
+                masks_d = segment.threshold_masks(evecs_d, threshold, which=1)
             if multi_region_dir:
-                ks = [segment.adaptive_num_clusters(evals[j].numpy()) if adaptive else non_adaptive_num_segments
-                      for j in range(len(items))]
-                labels = segment.kmeans_labels(kept["evecs"][:, 1:], ks, (Hp, Wp), infer_bg_index,
-                                               image_keys=[it[2] for it in items])[0].cpu().numpy()
-            k_cpu = k.cpu() if features_dir else None
+                if adaptive:   # the per-image cluster count comes from the eigenvalues (host arithmetic on K numbers)
+                    ks = [segment.adaptive_num_clusters(e.numpy()) for e in evals_d.cpu()]
+                else:
+                    ks = [non_adaptive_num_segments] * len(items)
+                labels_d = segment.kmeans_labels(evecs_d[:, 1:], ks, (Hp, Wp), infer_bg_index,
+                                                 image_keys=[it[2] for it in items])[0]
+
+            def to_host(t):
+                if t is None:
+                    return None
+                h_ = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h_.copy_(t, non_blocking=True)
+                return h_
+            h = {"items": items, "H": H, "W": W, "Hp": Hp, "Wp": Wp, "solve": solve, "evals": to_host(evals_d),
+                 "evecs": to_host(evecs_d), "info": to_host(info_d), "masks": to_host(masks_d), "labels": to_host(labels_d),
+                 "k": to_host(k) if features_dir else None, "keep": (k, evals_d, evecs_d, info_d, masks_d, labels_d)}
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            h["event"] = ev
             tc = time.perf_counter()
-            all_failed.extend(items[j][1] for j in failed)
-            if features_dir:
-                wr.submit_batch({"k": k_cpu.numpy()}, [it_ for j, it_ in enumerate(_feature_items(
-                    features_dir, [(it[1], it[2]) for it in items], model_name, patch_size, H, W)) if j not in failed])
-            wr.submit_batch({"evals": evals.numpy(), "evecs": evecs.numpy()},
-                            _eigs_items(eigs_dir, [it[1][:-4] for it in items], skip=failed))
-            for j, (_, file, index) in enumerate(items):
-                if j in failed:
-                    continue
-                if masks is not None:
-                    png_pool.submit(_save_png, masks[j].reshape(Hp, Wp).copy(), str(Path(single_region_dir) / f"{Path(file).stem}.png"))
-                if labels is not None:
-                    png_pool.submit(_save_png, labels[j].reshape(Hp, Wp).copy(), str(Path(multi_region_dir) / f"{Path(file).stem}.png"))
-            td = time.perf_counter()
             tm["stage"] += tb - ta
-            tm["gpu"] += tc - tb
-            tm["submit"] += td - tc
+            tm["launch"] += tc - tb
+            in_flight.append(h)
+            while len(in_flight) > 1:
+                finish(in_flight.pop(0))
 
         batcher = _Batcher(batch_size, flush)
         todo = []
@@ -571,11 +608,14 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
         for image, file, index in io_pipeline.ImagePrefetcher(dataset.__getitem__, todo, num_workers):
             batcher.add((int(image.shape[0]), int(image.shape[1])), (image, file, index))
         batcher.finish()
+        while in_flight:
+            finish(in_flight.pop(0))
     seconds = time.perf_counter() - t_start
     print(f"Saved eigs to {eigs_dir} ({len(todo)} images in {seconds:.2f}s after model set-up: "
-          f"{len(todo) / max(seconds, 1e-9):.0f} images/s incl. decode and file writes)")
+          f"{len(todo) / max(seconds, 1e-9):.0f} images/s incl. decode and file writes; main thread: "
+          + ", ".join(f"{k_} {v_:.2f}s" for k_, v_ in tm.items()) + ")")
     if all_failed:
         raise _lib.DssError(f"eigensolver did not converge for {len(all_failed)} image(s): {all_failed[:8]}")
     return {"images": len(todo), "seconds": seconds, "images_per_s": len(todo) / max(seconds, 1e-9),
-            "main_thread_seconds": {"pinned_staging": tm["stage"], "gpu_and_readback": tm["gpu"], "writer_submit": tm["submit"],
-                                    "until_writers_done": seconds}}
+            "main_thread_seconds": {"pinned_staging": tm["stage"], "kernel_launches": tm["launch"],
+                                    "waiting_for_gpu": tm["wait_gpu"], "writer_submit": tm["submit"], "total": seconds}}

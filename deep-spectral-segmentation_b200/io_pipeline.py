@@ -67,13 +67,15 @@ class PinnedRing:
     into the next slot (host memcpy), ``to_device`` starts the asynchronous H2D copy and returns the device batch; a
     slot is reused only after the copy that read it has completed (tracked with a CUDA event)."""
 
-    def __init__(self, shape: Tuple[int, int], capacity: int, device, slots: int = 2):
+    def __init__(self, shape: Tuple[int, int], capacity: int, device, slots: int = 2, copy_threads: int = 6):
         H, W = shape
         self.device = device
         # torch.empty(pin_memory=True) allocates page-locked memory directly (no pageable copy first)
         self.bufs = [torch.empty(capacity, H, W, 3, dtype=torch.uint8, pin_memory=True) for _ in range(slots)]
         self.events: List[Optional[torch.cuda.Event]] = [None] * slots
         self.next = 0
+        self.copy_threads = copy_threads
+        self._pool = ThreadPoolExecutor(copy_threads, thread_name_prefix="dss-stage") if copy_threads > 1 else None
 
     def stage(self, images: Sequence[torch.Tensor]) -> Tuple[int, torch.Tensor]:
         slot = self.next
@@ -81,8 +83,16 @@ class PinnedRing:
         if self.events[slot] is not None:
             self.events[slot].synchronize()
         buf = self.bufs[slot][:len(images)]
-        for j, im in enumerate(images):
-            buf[j].copy_(im)
+        if self._pool is None or len(images) < 2 * self.copy_threads:
+            for j, im in enumerate(images):
+                buf[j].copy_(im)
+        else:   # the memcpy into page-locked memory releases the interpreter lock: split it over a few threads
+            n = self.copy_threads
+
+            def part(t):
+                for j in range(t, len(images), n):
+                    buf[j].copy_(images[j])
+            list(self._pool.map(part, range(n)))
         return slot, buf
 
     def to_device(self, slot: int, host_batch: torch.Tensor) -> torch.Tensor:
@@ -174,7 +184,7 @@ def _materialise(arrays, j, extra, fields):
     return obj
 
 
-def _writer_process_main(q, errq):
+def _writer_process_main(q, errq, doneq):
     torch.set_num_threads(1)
     try:
         while True:
@@ -187,6 +197,7 @@ def _writer_process_main(q, errq):
                 tmp = f"{path}.tmp{os.getpid()}"
                 torch.save(_materialise(arrays, j, extra, fields), tmp)
                 os.replace(tmp, path)
+            doneq.put(len(items))
     except BaseException as e:  # noqa: BLE001
         import traceback
         errq.put(f"{e!r}\n{traceback.format_exc()}")
@@ -197,22 +208,28 @@ class ProcessWriter:
     arrays with a leading batch dimension (sent once per batch), ``items`` is a list of (path, row j, extra dict, fields)
     where fields maps dict keys to ("slice" | "slice1" | "np_slice", array name) or ("tensor0d", int); the worker builds
     each dict and torch.saves it. Started with the 'spawn' method (no fork of a process that holds a CUDA context and
-    running threads); start it early -- importing torch in the children takes a second or two."""
+    running threads). Importing torch in the children takes a second or two, so the pool is PERSISTENT: make_writer()
+    hands out the same processes to every command of this interpreter; ``close()`` only waits until everything that
+    was submitted has been written (``flush``)."""
 
-    def __init__(self, num_procs: int = 4, max_pending: int = 8):
+    def __init__(self, num_procs: int = 4, max_pending: int = 16):
         import multiprocessing as mp
         ctx = mp.get_context("spawn")
         self.q = ctx.Queue(max_pending)
         self.errq = ctx.Queue()
-        self.procs = [ctx.Process(target=_writer_process_main, args=(self.q, self.errq), daemon=True)
+        self.doneq = ctx.Queue()
+        self.procs = [ctx.Process(target=_writer_process_main, args=(self.q, self.errq, self.doneq), daemon=True)
                       for _ in range(max(1, num_procs))]
         for p_ in self.procs:
             p_.start()
-        self.files = 0
+        self.submitted = 0
+        self.done = 0
 
     def _check(self):
         if not self.errq.empty():
             raise RuntimeError("writer process failed: " + self.errq.get())
+        if any(not p_.is_alive() for p_ in self.procs):
+            raise RuntimeError("a writer process died")
 
     def submit_batch(self, arrays, items) -> None:
         self._check()
@@ -222,32 +239,50 @@ class ProcessWriter:
             part = items[w::n]
             if part:
                 self.q.put((arrays, part))
-        self.files += len(items)
+                self.submitted += len(part)
+
+    def flush(self, timeout: float = 600.0) -> int:
+        import queue as _q
+        import time as _t
+        t0 = _t.monotonic()
+        while self.done < self.submitted:
+            try:
+                self.done += self.doneq.get(timeout=0.5)
+            except _q.Empty:
+                self._check()
+                if _t.monotonic() - t0 > timeout:
+                    raise RuntimeError("writer processes did not finish in time")
+        self._check()
+        return self.done
 
     def close(self) -> int:
+        return self.flush()
+
+    def shutdown(self):
         for _ in self.procs:
             self.q.put(None)
         for p_ in self.procs:
-            p_.join()
-        self._check()
-        return self.files
+            p_.join(timeout=10)
 
     def __enter__(self):
         return self
 
     def __exit__(self, exc_type, exc, tb):
         if exc_type is None:
-            self.close()
-        else:
-            for p_ in self.procs:
-                p_.terminate()
+            self.flush()
         return False
+
+
+_WRITER_POOL = {}
 
 
 def make_writer(kind: str = "process", workers: int = 4):
     """'process' (default: writer processes, one message per batch) or 'thread' (torch.save on threads of this process)."""
     if kind == "process":
-        return ProcessWriter(workers)
+        pool = _WRITER_POOL.get(workers)
+        if pool is None or any(not p_.is_alive() for p_ in pool.procs):
+            pool = _WRITER_POOL[workers] = ProcessWriter(workers)
+        return pool
     if kind == "thread":
         return AsyncWriter(workers)
     raise ValueError(f"unknown writer kind {kind!r}")

@@ -13,8 +13,9 @@ torch.set_grad_enabled(False)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
-pipe = pipeline.SpectralPipeline("dino_vits16", K=5, device=dev, vit_batch=32)
-imgs = synth.blobs_batch(8, 480, 480, 0).repeat(B // 8, 1, 1, 1).to(dev)
+vb = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+pipe = pipeline.SpectralPipeline("dino_vits16", K=5, device=dev, vit_batch=vb)
+imgs = synth.blobs_batch(8, 480, 480, 0).repeat((B + 7) // 8, 1, 1, 1)[:B].contiguous().to(dev)
 for _ in range(passes):
     pipe.run_device(imgs)
 torch.cuda.synchronize()

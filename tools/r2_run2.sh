@@ -1,0 +1,27 @@
+#!/bin/bash
+# Round 2, GPU call 2: test suite with the fused-LN GEMM, ncu --set full of the kernels under work, LN fusion A/B bench.
+mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=600 --timeout-method=thread -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/summary.txt
+prof() {  # name, kernel regex, skip
+  timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c 1 -f -o gpurun_out/prof_$1 python tools/ncu_target.py 296 2 296 > gpurun_out/ncu_$1.log 2>&1
+  echo "ncu $1 exit $?" >> gpurun_out/summary.txt
+  python tools/ncu_summary.py report gpurun_out/prof_$1.ncu-rep > gpurun_out/ncu_$1.txt 2>&1
+}
+prof affinity 'gemm_f16_tcgen05_kernel<100' 1
+prof eigsh 'lanczos_laplacian_kernel' 1
+prof gemm_ln_fc1 'gemm_ln_f16_tcgen05_kernel<true' 12
+prof gemm_ln_qkv 'gemm_ln_f16_tcgen05_kernel<false' 12
+prof attention 'attention_tcgen05_kernel' 12
+prof gemm_proj 'gemm_f16_tcgen05_kernel<2, 192' 24
+DSS_VIT_FUSED_LN=0 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_unfused.json 2> gpurun_out/bench_unfused.err; echo "bench_unfused exit $?" >> gpurun_out/summary.txt
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_fused.json 2> gpurun_out/bench_fused.err; echo "bench_fused exit $?" >> gpurun_out/summary.txt
+timeout 600 python bench.py --no-cpu-baseline --images-per-step 294 > gpurun_out/bench_fused294.json 2> gpurun_out/bench_fused294.err; echo "bench_fused294 exit $?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt; tail -25 gpurun_out/pytest_gpu.log
+for f in unfused fused fused294; do python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_$f.json").read().strip().splitlines()[-1])
+    print("$f", round(d["value"]), round(d["e2e"]["value"]), [(k["kernel"], round(k["total_ms"]/4,2), k.get("frac")) for k in d["kernels"][:10]])
+except Exception as e: print("$f", e)
+PY
+done
