@@ -405,43 +405,41 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   return r;
 }
 
-// Exact-erf GELU x * Phi(x), Phi(x) = 0.5 + 0.5 erf(x / sqrt 2), branch-free and entirely on the FMA pipe (no MUFU):
-//   u = clamp(x / sqrt 2, -3, 3),  erf(u) ~= u P(u^2),  P = degree-8 minimax polynomial with the constraint 3 P(9) = 1
-// (so the clamped tails give Phi = 0 / 1 up to rounding). |erf error| <= 2.2e-5 -> |gelu error| <= 5.5e-5 absolute over
-// the whole fp32 range (tests/test_cpu_oracle.py evaluates this arithmetic in float32 against torch's float64 GELU);
-// the value is then rounded to fp16 (relative 4.9e-4). The previous formulation (Abramowitz-Stegun 7.1.26: one MUFU.RCP
-// and one MUFU.EX2 per element, ~14 scalar FMA-pipe instructions) made the fc1 epilogue longer than the tile's MMAs:
-// ncu showed the XU pipe at 38 % against 27 % for the tensor pipe. This one is 6.5 packed FMA-pipe + 2 ALU-pipe
-// instructions per element.
-#define DSS_GELU_C0 1.1283442974090576f
-#define DSS_GELU_C1 -0.3756363093852997f
-#define DSS_GELU_C2 0.11151406913995743f
-#define DSS_GELU_C3 -0.02537871152162552f
-#define DSS_GELU_C4 0.004330660682171583f
-#define DSS_GELU_C5 -0.0005299976910464466f
-#define DSS_GELU_C6 4.3234955228399485e-05f
-#define DSS_GELU_C7 -2.078214947687229e-06f
-#define DSS_GELU_C8 4.413194432117962e-08f
-#define DSS_GELU_CLAMP 3.0f
+// Exact-erf GELU, branch-free:  gelu(x) = x Phi(x) = relu(x) - |x| q(|x|),  q(a) = 0.5 erfc(a / sqrt 2) = 2^P(u),
+// u = min(a / sqrt 2, 5), P = degree-4 minimax fit of log2(erfc(u)) - 1 on [0, 5] weighted by the error it causes in
+// gelu (|x| q ln 2 dP). Max |gelu error| 6.4e-6 over the whole fp32 range, relative error <= 1e-3 for x >= -3
+// (tests/test_cpu_host.py emulates this arithmetic in float32 against torch's float64 GELU); the value is then rounded
+// to fp16 (relative 4.9e-4, smallest normal 6.1e-5).
+// Cost per element: 7 FMA-pipe lane operations (bias add, scale, 4 Horner steps, final fma -- issued as packed FFMA2),
+// one MUFU.EX2 and three ALU-pipe operations (sign, min, max), spread over three pipes. History: Abramowitz-Stegun
+// 7.1.26 (round 1: MUFU.RCP + MUFU.EX2 + ~14 scalar FMA-pipe instructions; ncu XU pipe 38 % vs tensor pipe 27 %) ->
+// u P(u^2) erf polynomial of degree 8 on the FMA pipe only (14 lane operations: ncu showed the epilogue warps stalled on
+// the FMA pipe, 2 500 cycles per 128 x 64 box against 2 300 cycles of MMA per tile; packed FFMA2 with register operands
+// issues at the same lane rate as scalar FFMA) -> this form.
+#define DSS_GELU_P0 -1.0004795789718628f
+#define DSS_GELU_P1 -1.6226296424865723f
+#define DSS_GELU_P2 -0.9360293745994568f
+#define DSS_GELU_P3 -0.12467514723539352f
+#define DSS_GELU_P4 0.015465063974261284f
+#define DSS_GELU_CLAMP 5.0f
 __device__ __forceinline__ void gelu_erf_x2(float x0, float x1, float& y0, float& y1) {
-  const uint64_t x = pack_f32x2(x0, x1);
+  const float na0 = __uint_as_float(__float_as_uint(x0) | 0x80000000u);   // -|x|
+  const float na1 = __uint_as_float(__float_as_uint(x1) | 0x80000000u);
+  const uint64_t na = pack_f32x2(na0, na1);
   float u0, u1;
-  unpack_f32x2(mul_f32x2(x, pack_f32x2(0.70710678118654752440f, 0.70710678118654752440f)), u0, u1);
-  u0 = fmaxf(fminf(u0, DSS_GELU_CLAMP), -DSS_GELU_CLAMP);
-  u1 = fmaxf(fminf(u1, DSS_GELU_CLAMP), -DSS_GELU_CLAMP);
+  unpack_f32x2(mul_f32x2(na, pack_f32x2(-0.70710678118654752440f, -0.70710678118654752440f)), u0, u1);
+  u0 = fminf(u0, DSS_GELU_CLAMP);
+  u1 = fminf(u1, DSS_GELU_CLAMP);
   const uint64_t u = pack_f32x2(u0, u1);
-  const uint64_t s = mul_f32x2(u, u);
-  uint64_t p = fma_f32x2(pack_f32x2(DSS_GELU_C8, DSS_GELU_C8), s, pack_f32x2(DSS_GELU_C7, DSS_GELU_C7));
-  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C6, DSS_GELU_C6));
-  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C5, DSS_GELU_C5));
-  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C4, DSS_GELU_C4));
-  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C3, DSS_GELU_C3));
-  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C2, DSS_GELU_C2));
-  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C1, DSS_GELU_C1));
-  p = fma_f32x2(p, s, pack_f32x2(DSS_GELU_C0, DSS_GELU_C0));
-  const uint64_t e = mul_f32x2(u, p);                                              // erf(x / sqrt 2)
-  const uint64_t phi = fma_f32x2(e, pack_f32x2(0.5f, 0.5f), pack_f32x2(0.5f, 0.5f));
-  unpack_f32x2(mul_f32x2(x, phi), y0, y1);
+  uint64_t p = fma_f32x2(pack_f32x2(DSS_GELU_P4, DSS_GELU_P4), u, pack_f32x2(DSS_GELU_P3, DSS_GELU_P3));
+  p = fma_f32x2(p, u, pack_f32x2(DSS_GELU_P2, DSS_GELU_P2));
+  p = fma_f32x2(p, u, pack_f32x2(DSS_GELU_P1, DSS_GELU_P1));
+  p = fma_f32x2(p, u, pack_f32x2(DSS_GELU_P0, DSS_GELU_P0));
+  float p0, p1, q0, q1;
+  unpack_f32x2(p, p0, p1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(p0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(p1));
+  unpack_f32x2(fma_f32x2(na, pack_f32x2(q0, q1), pack_f32x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), y0, y1);
 }
 __device__ __forceinline__ float gelu_erf(float x) {
   float y0, y1;

@@ -27,6 +27,7 @@ constexpr int EIG_MAX_K = 64;
 
 constexpr int EIG_STRIP_CH = 4;                    // float4 column chunks per lane and strip
 constexpr int EIG_STRIP = 32 * 4 * EIG_STRIP_CH;   // 512 columns per strip
+constexpr int EIG_SMALL_N = 1024;                  // up to here two CTAs (images) share an SM: the <2, 2> instantiation
 
 struct EigParams {
   const float* W;     // [B, N, ldw]
@@ -539,7 +540,7 @@ static int eig_grid(int B, int Npad, int mmax) {
   const size_t smem = eig_smem_bytes(Npad, mmax);
   int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);  // 512 threads, <=64 regs => at most 2 CTAs / SM
-  if (Npad > EIG_STRIP) per_sm = 1;                     // the large-N instantiation is built for one CTA per SM
+  if (Npad > EIG_SMALL_N) per_sm = 1;                   // the large-N instantiation is built for one CTA per SM
   int g = sms * per_sm;
   return B < g ? B : g;
 }
@@ -587,7 +588,7 @@ static int eigsh_launch(const float* Wmat, const float* deg, int ldw, int B, int
     return DSS_ERR_UNSUPPORTED;
   }
   LaunchScope scope(static_cast<cudaStream_t>(stream), KC_EIGSH);
-  if (p.Npad <= EIG_STRIP) {
+  if (p.Npad <= EIG_SMALL_N) {
     DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lanczos_laplacian_kernel<2, 2><<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   } else {

@@ -333,7 +333,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t stage_u32 = base + STAGES * STAGE_BYTES;
       int lt = 0, cc = 0;
       [[maybe_unused]] float aff_rowsum = 0.f;       // affinity: this thread's row sum over the tile's columns
-      [[maybe_unused]] float aff_mx = 1.f, aff_unscale = 1.f;
+      [[maybe_unused]] float aff_mx = 1.f, aff_rmx = 1.f, aff_unscale = 1.f;
       for (int t = cid; t < total_items; t += ncl, ++lt) {
         const TileCoord tc = decode_tile<BN>(t, pairs_m, tiles_n, rank, p.tri);
         const int buf = lt & 1;
@@ -376,6 +376,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             const int m = tc.m0 + row, n = nc + sl * W;
             if (b == 0) {   // per-tile constants (L2 round trips: not once per box)
               aff_mx = __uint_as_float(__ldg(p.img_max + tc.z));
+              aff_rmx = __frcp_rn(aff_mx);
               // un-normalised features were pre-scaled by pre = 2^-ceil(log2 max|f|) (affinity.cu): the scale cancels
               // in W / max(W); when the division is skipped (which_matrix = 'affinity' / 'affinity_svd') it is undone
               aff_unscale = 1.0f;
@@ -384,14 +385,25 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (am > 0.f) aff_unscale = exp2f(2.0f * ceilf(log2f(am)));
               }
             }
-            const float mx = aff_mx, unscale = aff_unscale;
+            const float mx = aff_mx, rmx = aff_rmx, unscale = aff_unscale;
             const uint8_t* cnt = (p.counts && m < M) ? p.counts + ((long long)tc.z * M + m) * M + n : nullptr;
 #pragma unroll
             for (int e = 0; e < W; ++e) {
               float y = x[e];
               if (p.threshold & 1) y = y > 0.f ? y : 0.f;   // W * (W > 0)
-              if (!(p.threshold & 2)) y = y / mx;           // W / W.max()
-              else y *= unscale;
+              if (!(p.threshold & 2)) {                     // W / W.max()
+                // y / mx without the compiler's IEEE division subroutine: its range check sends zero and tiny numerators
+                // -- most of a thresholded affinity -- down a ~100-instruction slow path (ncu: 84 % of this kernel's
+                // 617 M warp instructions). mx is the largest Gram diagonal: exactly 1 for most normalised images
+                // (nothing to do), else q = y r, one residual correction: q + (y - q mx) r -- the correctly rounded
+                // quotient for these operand ranges (0 <= y <= ~mx, mx in the normal range).
+                if (mx != 1.0f) {
+                  const float q0 = y * rmx;
+                  y = fmaf(fmaf(-q0, mx, y), rmx, q0);
+                }
+              } else {
+                y *= unscale;
+              }
               if (cnt && n + e < M) y += static_cast<float>(cnt[e]) * p.lambda;   // + W_color * lambda
               x[e] = (n + e < M) ? y : 0.f;
             }

@@ -72,6 +72,7 @@ class PinnedRing:
         self.device = device
         # torch.empty(pin_memory=True) allocates page-locked memory directly (no pageable copy first)
         self.bufs = [torch.empty(capacity, H, W, 3, dtype=torch.uint8, pin_memory=True) for _ in range(slots)]
+        self.np_bufs = [b.numpy() for b in self.bufs]    # views of the page-locked memory
         self.events: List[Optional[torch.cuda.Event]] = [None] * slots
         self.next = 0
         self.copy_threads = copy_threads
@@ -83,15 +84,19 @@ class PinnedRing:
         if self.events[slot] is not None:
             self.events[slot].synchronize()
         buf = self.bufs[slot][:len(images)]
+        import numpy as np
+        dst = self.np_bufs[slot]
+        # numpy's copy loop releases the interpreter lock (torch's Tensor.copy_ on CPU tensors does not: measured 2.9 GB/s
+        # for the whole staging step with 32 decode threads competing for the lock), so a few threads copy in parallel
         if self._pool is None or len(images) < 2 * self.copy_threads:
             for j, im in enumerate(images):
-                buf[j].copy_(im)
-        else:   # the memcpy into page-locked memory releases the interpreter lock: split it over a few threads
+                np.copyto(dst[j], im.numpy())
+        else:
             n = self.copy_threads
 
             def part(t):
                 for j in range(t, len(images), n):
-                    buf[j].copy_(images[j])
+                    np.copyto(dst[j], images[j].numpy())
             list(self._pool.map(part, range(n)))
         return slot, buf
 

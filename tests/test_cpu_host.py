@@ -154,26 +154,25 @@ def test_attention_exp2_polynomial_constants():
 
 
 def test_gemm_gelu_erf_constants():
-    """The fc1 epilogue evaluates the exact-erf GELU on the FMA pipe: erf(u) = u P(u^2) on the clamped argument
-    (csrc/common.cuh, gelu_erf_x2). Emulate that float32 arithmetic with the constants parsed out of the kernel source
-    against torch's erf GELU in float64 over the whole range fp16 activations can take."""
+    """The fc1 epilogue evaluates the exact-erf GELU as relu(x) - |x| 2^P(min(|x| / sqrt 2, c)) (csrc/common.cuh,
+    gelu_erf_x2). Emulate that float32 arithmetic with the constants parsed out of the kernel source against torch's
+    erf GELU in float64 over the whole range fp16 activations can take."""
     import re
     src = (ROOT / "deep-spectral-segmentation_b200" / "csrc" / "common.cuh").read_text()
-    coef = [np.float32(float(v)) for v in re.findall(r"#define DSS_GELU_C\d (-?[\d.e+-]+)f", src)]
+    coef = [np.float32(float(v)) for v in re.findall(r"#define DSS_GELU_P\d (-?[\d.e+-]+)f", src)]
     clamp = np.float32(float(re.search(r"#define DSS_GELU_CLAMP ([\d.]+)f", src).group(1)))
-    assert len(coef) == 9, coef                            # c0 .. c8 of P(s) = sum c_k s^k
-    assert abs(float(clamp) * sum(float(c) * float(clamp) ** (2 * k) for k, c in enumerate(coef)) - 1.0) < 2e-6
+    assert len(coef) == 5, coef                            # p0 .. p4 of P(u) = sum p_k u^k
     x = np.concatenate([np.linspace(-12.0, 12.0, 480001), np.linspace(-6.0e4, 6.0e4, 20001)]).astype(np.float32)
-    u = np.clip((x * np.float32(0.7071067811865476)).astype(np.float32), -clamp, clamp)
-    s2 = (u * u).astype(np.float32)
-    p = np.full_like(s2, coef[8])
-    for k in range(7, -1, -1):
-        p = (p.astype(np.float64) * s2.astype(np.float64) + np.float64(coef[k])).astype(np.float32)   # one rounding = fma
-    e = (u * p).astype(np.float32)
-    phi = (e.astype(np.float64) * 0.5 + 0.5).astype(np.float32)
-    got = (x * phi).astype(np.float32).astype(np.float64)
+    na = -np.abs(x)
+    u = np.minimum((na * np.float32(-0.7071067811865476)).astype(np.float32), clamp)
+    p = np.full_like(u, coef[4])
+    for k in range(3, -1, -1):
+        p = (p.astype(np.float64) * u.astype(np.float64) + np.float64(coef[k])).astype(np.float32)   # one rounding = fma
+    q = np.exp2(p.astype(np.float64))
+    q = (q * (1.0 + 2.4e-7)).astype(np.float32)            # ex2.approx: 2 ulp
+    got = (na.astype(np.float64) * q.astype(np.float64) + np.maximum(x, np.float32(0)).astype(np.float64)).astype(np.float32)
     ref = torch.nn.functional.gelu(torch.from_numpy(x.astype(np.float64))).numpy()
-    err = np.abs(got - ref)
-    small = np.abs(x) <= 12
-    assert err[small].max() < 7e-5, err[small].max()        # 2.2e-5 on erf -> 1.1e-5 on Phi, times |x| <= 4.3 where it matters
-    assert np.all(err <= 7e-5 + 2e-6 * np.abs(x))           # clamped tails: Phi is 0 / 1 up to a few ulp
+    err = np.abs(got.astype(np.float64) - ref)
+    assert err.max() < 8e-6, err.max()
+    neg = (x < -1) & (x > -3)                               # relative accuracy down to -3 (values >= 4e-3; beyond that the
+    assert np.all(err[neg] <= 2e-3 * np.abs(ref[neg]))      # 6e-6 absolute bound is below the fp16 normal range)
