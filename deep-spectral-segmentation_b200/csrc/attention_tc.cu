@@ -281,41 +281,107 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
           const int kc = tail ? kc_last : FA_BN;
           const int nvalid = tail ? T - j * FA_BN : FA_BN;
           uint32_t v[128];
+          float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent maximum chains
+          uint64_t rs2[2] = {0ull, 0ull};                                 // packed partial row sums, two chains
+          // chunk c of the tile: (tail mask) -> running maximum of the raw scores -> P = 2^(s*c - m_ref*c) -> row sum
+          // -> packed fp16 pairs into TMEM (the A operand of the P V product). The maximum is tracked alongside the
+          // exponentials (FMNMX3 on the ALU pipe) instead of in a pass of its own.
+          auto chunk = [&](const int c, const float msc, const bool track_max) {
+            if (tail) {   // keys beyond T: score -inf -> probability exactly 0
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (c * 32 < kc) tmem_ld_32x32(s_col + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&v[c * 32]));
-          tmem_ld_wait();
-          FA_TRACE(tb + 1);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free(g));   // S_g is in registers: the next score tile may overwrite it
-          float mxc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c * 32 < kc) {
-              if (tail) {   // keys beyond T: score -inf -> probability exactly 0
-#pragma unroll
-                for (int i = c * 32; i < c * 32 + 32; ++i)
-                  if (i >= nvalid) v[i] = 0xff800000u;
-              }
+              for (int i = c * 32; i < c * 32 + 32; ++i)
+                if (i >= nvalid) v[i] = 0xff800000u;
+            }
+            if (track_max) {
 #pragma unroll
               for (int i = c * 32; i < c * 32 + 32; ++i)
                 if (!(ABL & 4)) mxc[i & 3] = fmaxf(mxc[i & 3], __uint_as_float(v[i]));
             }
-          }
-          const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
-          FA_TRACE(tb + 2);
-          // P_g is single buffered and O_g accumulates in place: P_g V_{j-1} must be complete (issued long ago)
-          if (j > 0) {
+            const uint64_t sc2 = pack_f32x2(sc, sc), nmsc2 = pack_f32x2(-msc, -msc);
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const int i = c * 32 + e;
+              float x0, x1;
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nmsc2), x0, x1);
+              constexpr int npoly = (ABL & 1024) ? 0 : ((ABL >> 8) & 3) ? ((ABL >> 8) & 3) : FA_POLY_OF_4;
+              float p0, p1;
+              if (((e >> 1) & 3) < npoly) {
+                ex2_poly_x2(x0, x1, p0, p1);
+              } else {
+                p0 = (ABL & 1) ? x0 : ex2_approx(x0);
+                p1 = (ABL & 1) ? x1 : ex2_approx(x1);
+              }
+              if (!(ABL & 32)) rs2[(e >> 1) & 1] = add_f32x2(rs2[(e >> 1) & 1], pack_f32x2(p0, p1));
+              pk[e >> 1] = pack_half2(p0, p1);
+            }
+            if (!(ABL & 2)) tmem_st_32x16(p_col + c * 16, pk);
+            else rs2[0] += pk[0] ^ pk[5] ^ pk[10] ^ pk[15];   // keep the values alive
+          };
+          if (j == 0) {
+            // ---- first key tile of the item: no reference maximum yet, so the row maximum comes first
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c * 32 < kc) tmem_ld_32x32(s_col + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&v[c * 32]));
+            tmem_ld_wait();
+            FA_TRACE(tb + 1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free(g));   // S_g is in registers: the next score tile may overwrite it
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c * 32 < kc) {
+#pragma unroll
+                for (int i = c * 32; i < c * 32 + 32; ++i) {
+                  if (tail && i >= nvalid) v[i] = 0xff800000u;
+                  if (!(ABL & 4)) mxc[i & 3] = fmaxf(mxc[i & 3], __uint_as_float(v[i]));
+                }
+              }
+            }
+            m_ref = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
+            FA_TRACE(tb + 2);
+            FA_TRACE(tb + 3);
+            const float msc = m_ref * sc;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c * 32 < kc) {
+                chunk(c, msc, false);
+                // release tile B's first key tile when tile A is half way through its first exponentials: the two
+                // groups then stay about half a period apart (one in its MUFU phase, the other loading / reducing)
+                if (c == 1 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+              }
+            }
+            if (kc <= 32 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // (short first tile)
+          } else {
+            // ---- later key tiles: exponentials are taken relative to the reference maximum of the EARLIER tiles right
+            // away (softmax is shift invariant; fp16 P and the fp32 sums have 2^8 of headroom), chunk 0 while the TMEM
+            // loads of chunks 1-3 are still in flight; only if this tile turns out to exceed the reference by more than
+            // 2^8 is the reference raised and the tile redone (rare).
+            tmem_ld_32x32(s_col, *reinterpret_cast<uint32_t (*)[32]>(&v[0]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+              if (c * 32 < kc) tmem_ld_32x32(s_col + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&v[c * 32]));
+            FA_TRACE(tb + 1);
+            // P_g is single buffered and O_g accumulates in place: P_g V_{j-1} must be complete (issued long ago)
             mbar_wait(o_full(g), (m - 1) & 1);
             tc_fence_after();
-          }
-          if (j == 0) {
-            m_ref = mx;
-          } else {
+            FA_TRACE(tb + 2);
+            float msc = m_ref * sc;
+            chunk(0, msc, true);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free(g));   // S_g is in registers: the next score tile may overwrite it
+            FA_TRACE(tb + 3);
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+              if (c * 32 < kc) chunk(c, msc, true);
+            const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
             const bool raise = (mx - m_ref) * sc > FA_RESCALE_LOG2;
-            if (__any_sync(0xffffffffu, raise)) {   // rare: rescale this warp's rows of O_g in TMEM
+            if (__any_sync(0xffffffffu, raise)) {   // rare: rescale this warp's rows of O_g in TMEM, redo the tile
               const float f = raise ? ex2_approx((m_ref - mx) * sc) : 1.0f;
+              tmem_st_wait();
               uint32_t t[32];
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
@@ -328,41 +394,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
               tmem_st_wait();
               l_run *= f;
               if (raise) m_ref = mx;
+              msc = m_ref * sc;
+              rs2[0] = rs2[1] = 0ull;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c * 32 < kc) chunk(c, msc, false);
             }
           }
-          FA_TRACE(tb + 3);
-          const float msc = m_ref * sc;
-          // ---- P = 2^(s*c - m*c), row sum, P as packed fp16 pairs into TMEM (the A operand of the P V product)
-          const uint64_t sc2 = pack_f32x2(sc, sc), nmsc2 = pack_f32x2(-msc, -msc);
-          uint64_t rs2[2] = {0ull, 0ull};   // packed partial row sums, two independent chains
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c * 32 < kc) {
-              uint32_t pk[16];
-#pragma unroll
-              for (int e = 0; e < 32; e += 2) {
-                const int i = c * 32 + e;
-                float x0, x1;
-                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nmsc2), x0, x1);
-                constexpr int npoly = (ABL & 1024) ? 0 : ((ABL >> 8) & 3) ? ((ABL >> 8) & 3) : FA_POLY_OF_4;
-                float p0, p1;
-                if (((e >> 1) & 3) < npoly) {
-                  ex2_poly_x2(x0, x1, p0, p1);
-                } else {
-                  p0 = (ABL & 1) ? x0 : ex2_approx(x0);
-                  p1 = (ABL & 1) ? x1 : ex2_approx(x1);
-                }
-                if (!(ABL & 32)) rs2[(e >> 1) & 1] = add_f32x2(rs2[(e >> 1) & 1], pack_f32x2(p0, p1));
-                pk[e >> 1] = pack_half2(p0, p1);
-              }
-              if (!(ABL & 2)) tmem_st_32x16(p_col + c * 16, pk);
-              else rs2[0] += pk[0] ^ pk[5] ^ pk[10] ^ pk[15];   // keep the values alive
-              // release tile B's first key tile when tile A is half way through its first exponentials: the two
-              // groups then stay about half a period apart (one in its MUFU phase, the other loading / reducing)
-              if (c == 1 && j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
-            }
-          }
-          if (kc <= 32 && j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // (short first tile)
           float rs, rs_hi;
           unpack_f32x2(add_f32x2(rs2[0], rs2[1]), rs, rs_hi);
           rs += rs_hi;

@@ -16,6 +16,7 @@
 // The Lanczos basis lives in a per-CTA global scratch (L2), the working vectors in shared memory. Ritz values of the tridiagonal matrix come from a 32-way
 // Sturm multisection in fp64 (one warp per eigenvalue), Ritz vectors from a twisted factorisation.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -100,6 +101,7 @@ __host__ __device__ inline size_t eig_double_bytes(int mmax) {
 template <int R, int MINB>
 __global__ void __launch_bounds__(EIG_THREADS, MINB)
 lanczos_laplacian_kernel(EigParams p) {
+  constexpr int PRE = MINB == 2 ? 2 : EIG_STRIP_CH;   // column blocks whose loads are in flight together
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int N = p.N, Npad = p.Npad, mmax = p.mmax, K = p.K, ldw = p.ldw;
   const bool lapn = p.mode == 0, plain = p.mode == 2;
@@ -246,44 +248,57 @@ lanczos_laplacian_kernel(EigParams p) {
             const int cb = s0 >> 2, nch = s1 >> 2;
             const int k_first = chd > cb ? (chd - cb) >> 5 : 0;
             const int k_end = ((s1 - s0) + 127) >> 7;
+            // Groups of PRE blocks: all of a group's loads (PRE x R independent 128-bit loads per lane) are issued before
+            // any of them is consumed -- with one block at a time the warps stalled on the first FFMA of every block
+            // (55 % of the stall samples) at 46 % of the DRAM peak: not enough bytes in flight.
 #pragma unroll
-            for (int k = 0; k < EIG_STRIP_CH; ++k) {
-              if (k < k_first || k >= k_end) continue;       // (uniform)
-              const int ch = cb + lane + 32 * k;             // this lane's k-th chunk of the strip: columns 4 ch .. 4 ch + 3
-              if (ch >= chd && ch < nch) {
+            for (int k0 = 0; k0 < EIG_STRIP_CH; k0 += PRE) {
+              if (k0 + PRE <= k_first || k0 >= k_end) continue;   // (uniform) nothing of this group right of the diagonal
+              float4 u[PRE][R];
+              bool act[PRE];
+#pragma unroll
+              for (int kk = 0; kk < PRE; ++kk) {
+                const int k = k0 + kk;
+                const int ch = cb + lane + 32 * k;           // this lane's chunk of block k: columns 4 ch .. 4 ch + 3
+                act[kk] = k >= k_first && k < k_end && ch >= chd && ch < nch;
+#pragma unroll
+                for (int q = 0; q < R; ++q) u[kk][q] = act[kk] ? __ldg(rowp[q] + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int kk = 0; kk < PRE; ++kk) {
+                const int k = k0 + kk;
+                if (k < k_first || k >= k_end) continue;     // (uniform)
+                const int ch = cb + lane + 32 * k;
+                if (!act[kk]) continue;
                 const float4 x = x4[ch];
-                float4 u[R];
+                if (k == k_first && ch == chd) {             // the chunk that holds the diagonal elements of these rows
 #pragma unroll
-                for (int q = 0; q < R; ++q) u[q] = __ldg(rowp[q] + ch);
-                if (k == k_first) {                          // (uniform) the block that holds the diagonal chunk
-                  if (ch == chd) {
+                  for (int q = 0; q < R; ++q) {
                     // row part: drop the elements left of the diagonal; column part: drop the diagonal as well
-                    float4 c[R];
-#pragma unroll
-                    for (int q = 0; q < R; ++q) {
-                      const int dq = (r + q) & 3;
-                      if (dq > 0) u[q].x = 0.f;
-                      if (dq > 1) u[q].y = 0.f;
-                      if (dq > 2) u[q].z = 0.f;
-                      c[q] = u[q];
-                      if (dq == 0) c[q].x = 0.f;
-                      if (dq == 1) c[q].y = 0.f;
-                      if (dq == 2) c[q].z = 0.f;
-                      if (dq == 3) c[q].w = 0.f;
-                      acc[q] = fmaf(u[q].x, x.x, acc[q]); acc[q] = fmaf(u[q].y, x.y, acc[q]);
-                      acc[q] = fmaf(u[q].z, x.z, acc[q]); acc[q] = fmaf(u[q].w, x.w, acc[q]);
-                      colacc[k].x = fmaf(c[q].x, xr[q], colacc[k].x); colacc[k].y = fmaf(c[q].y, xr[q], colacc[k].y);
-                      colacc[k].z = fmaf(c[q].z, xr[q], colacc[k].z); colacc[k].w = fmaf(c[q].w, xr[q], colacc[k].w);
-                    }
-                    continue;
+                    const int dq = (r + q) & 3;
+                    float4 a = u[kk][q];
+                    if (dq > 0) a.x = 0.f;
+                    if (dq > 1) a.y = 0.f;
+                    if (dq > 2) a.z = 0.f;
+                    float4 c = a;
+                    if (dq == 0) c.x = 0.f;
+                    if (dq == 1) c.y = 0.f;
+                    if (dq == 2) c.z = 0.f;
+                    if (dq == 3) c.w = 0.f;
+                    acc[q] = fmaf(a.x, x.x, acc[q]); acc[q] = fmaf(a.y, x.y, acc[q]);
+                    acc[q] = fmaf(a.z, x.z, acc[q]); acc[q] = fmaf(a.w, x.w, acc[q]);
+                    colacc[k].x = fmaf(c.x, xr[q], colacc[k].x); colacc[k].y = fmaf(c.y, xr[q], colacc[k].y);
+                    colacc[k].z = fmaf(c.z, xr[q], colacc[k].z); colacc[k].w = fmaf(c.w, xr[q], colacc[k].w);
                   }
-                }
+                } else {
 #pragma unroll
-                for (int q = 0; q < R; ++q) {
-                  acc[q] = fmaf(u[q].x, x.x, acc[q]); acc[q] = fmaf(u[q].y, x.y, acc[q]);
-                  acc[q] = fmaf(u[q].z, x.z, acc[q]); acc[q] = fmaf(u[q].w, x.w, acc[q]);
-                  colacc[k].x = fmaf(u[q].x, xr[q], colacc[k].x); colacc[k].y = fmaf(u[q].y, xr[q], colacc[k].y);
-                  colacc[k].z = fmaf(u[q].z, xr[q], colacc[k].z); colacc[k].w = fmaf(u[q].w, xr[q], colacc[k].w);
+                  for (int q = 0; q < R; ++q) {
+                    const float4 a = u[kk][q];
+                    acc[q] = fmaf(a.x, x.x, acc[q]); acc[q] = fmaf(a.y, x.y, acc[q]);
+                    acc[q] = fmaf(a.z, x.z, acc[q]); acc[q] = fmaf(a.w, x.w, acc[q]);
+                    colacc[k].x = fmaf(a.x, xr[q], colacc[k].x); colacc[k].y = fmaf(a.y, xr[q], colacc[k].y);
+                    colacc[k].z = fmaf(a.z, xr[q], colacc[k].z); colacc[k].w = fmaf(a.w, xr[q], colacc[k].w);
+                  }
                 }
               }
             }
@@ -540,7 +555,8 @@ static int eig_grid(int B, int Npad, int mmax) {
   const size_t smem = eig_smem_bytes(Npad, mmax);
   int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
   per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);  // 512 threads, <=64 regs => at most 2 CTAs / SM
-  if (Npad > EIG_SMALL_N) per_sm = 1;                   // the large-N instantiation is built for one CTA per SM
+  static const int variant = [] { const char* e = getenv("DSS_EIG_VARIANT"); return e ? atoi(e) : 0; }();
+  if ((Npad > EIG_SMALL_N && variant != 1) || variant == 2) per_sm = 1;   // the <4, 1> instantiation: one CTA per SM
   int g = sms * per_sm;
   return B < g ? B : g;
 }
@@ -588,7 +604,8 @@ static int eigsh_launch(const float* Wmat, const float* deg, int ldw, int B, int
     return DSS_ERR_UNSUPPORTED;
   }
   LaunchScope scope(static_cast<cudaStream_t>(stream), KC_EIGSH);
-  if (p.Npad <= EIG_SMALL_N) {
+  static const int variant = [] { const char* e = getenv("DSS_EIG_VARIANT"); return e ? atoi(e) : 0; }();   // tuning
+  if ((p.Npad <= EIG_SMALL_N && variant != 2) || variant == 1) {
     DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lanczos_laplacian_kernel<2, 2><<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   } else {

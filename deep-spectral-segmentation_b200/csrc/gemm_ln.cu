@@ -167,7 +167,6 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       }
     }
   } else if (warp < 4 + LG_EPI_WARPS) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     // ---- epilogue: all 16 warps cooperate on one 64-column output box at a time (gemm.cu's TMA-store path)
     const int ew = warp - 4;
     const int q = warp & 3, sl = ew >> 2;
@@ -228,22 +227,25 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     }
     if (issuer) tma_store_wait_all<0>();
   } else {
-    // ---- LayerNorm producers: warp w owns rows [16 w, 16 w + 16) of the block
+    // ---- LayerNorm producers: warp w owns rows [16 w, 16 w + 16) of the block. They get the registers the service
+    // warps gave up: 4 rows x 3 float4 per lane in flight in the statistics pass (the first, HBM, read of x) -- with 2
+    // rows in flight the 8 producer warps could not pull a 196 KB block in less time than its MMAs take
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int w = warp - 4 - LG_EPI_WARPS;
     auto stats = [&](int m0, int par) {
-      // two-pass mean / variance like torch (and like the stand-alone kernel it replaces), 2 rows at a time
+      // two-pass mean / variance like torch (and like the stand-alone kernel it replaces), 4 rows at a time
 #pragma unroll 1
-      for (int rr = 0; rr < 16; rr += 2) {
-        float4 v[2][3];
+      for (int rr = 0; rr < 16; rr += 4) {
+        float4 v[4][3];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int m = m0 + w * 16 + rr + i;
           const float4* xr = reinterpret_cast<const float4*>(p.x + (long long)(m < p.M ? m : 0) * LG_K);
 #pragma unroll
           for (int j = 0; j < 3; ++j) v[i][j] = m < p.M ? xr[lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           float s = 0.f;
 #pragma unroll
           for (int j = 0; j < 3; ++j) s += (v[i][j].x + v[i][j].y) + (v[i][j].z + v[i][j].w);
