@@ -155,7 +155,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
     uint32_t ph = 0;   // K/V ring position, carried across items
     int qi = 0;        // item counter of this CTA
     for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++qi) {
-      const int qp = w % nq2, bh = w / nq2;
+      // item w -> (image * heads + head, pair of query tiles). The pair index is rotated by the (image, head) index:
+      // with the plain w % nq2 a CTA (w = blockIdx + k * 148, 148 % 4 == 0) would get the SAME pair index in every item,
+      // and the CTAs that only ever see the light last pair (a 5-row tail tile at T = 901) idle at the end of the
+      // kernel while the others are still on full pairs (ncu: 8.5 % of the stall samples on EXIT)
+      const int bh = w / nq2, qp = (w % nq2 + bh) % nq2;
       const int h = bh % heads, row0 = (bh / heads) * T;   // first row of this image in the [B*T, 3d] matrix
       const int qb = qi & 1;
       const uint32_t qph = (qi >> 1) & 1;
@@ -257,7 +261,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
     const float sc = 1.4426950408889634f * 0.125f;  // log2(e) / sqrt(64)
     uint32_t m = 0;   // key-tile step counter of this CTA (all barrier phases derive from it)
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-      const int qp = w % nq2, bh = w / nq2;
+      // item w -> (image * heads + head, pair of query tiles). The pair index is rotated by the (image, head) index:
+      // with the plain w % nq2 a CTA (w = blockIdx + k * 148, 148 % 4 == 0) would get the SAME pair index in every item,
+      // and the CTAs that only ever see the light last pair (a 5-row tail tile at T = 901) idle at the end of the
+      // kernel while the others are still on full pairs (ncu: 8.5 % of the stall samples on EXIT)
+      const int bh = w / nq2, qp = (w % nq2 + bh) % nq2;
       const int h = bh % heads;
       const int q0 = (2 * qp + g) * FA_BM;
       const bool dead = q0 >= T || ((ABL & 64) && g == 1);   // odd number of query tiles: nothing to do for B in the last pair

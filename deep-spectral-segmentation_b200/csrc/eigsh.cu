@@ -28,7 +28,11 @@ constexpr int EIG_MAX_K = 64;
 
 constexpr int EIG_STRIP_CH = 4;                    // float4 column chunks per lane and strip
 constexpr int EIG_STRIP = 32 * 4 * EIG_STRIP_CH;   // 512 columns per strip
-constexpr int EIG_SMALL_N = 1024;                  // up to here two CTAs (images) share an SM: the <2, 2> instantiation
+// Up to this N two CTAs (images) could share an SM with the <2, 2> instantiation (64 registers, 2 x 2 loads in flight per
+// lane). Measured on the 296-image step at N = 900 it loses to <4, 1> -- one CTA per SM, 128 registers, all 16 loads of
+// a row group's column blocks in flight per lane: 2.27 ms vs 1.94 ms -- so it is only kept for tuning
+// (DSS_EIG_VARIANT=1).
+constexpr int EIG_SMALL_N = 0;
 
 struct EigParams {
   const float* W;     // [B, N, ldw]

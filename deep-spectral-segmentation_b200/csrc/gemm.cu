@@ -340,10 +340,20 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(tfull_bar(buf), aph);
         tc_fence_after();
+        if constexpr (EPI == EPI_AFFINITY_F32) {
+          if (p.tri && tc.m0 > tc.n0) {
+            // the odd CTA's tile below the diagonal (computed only to keep the pair in lock step on the shared B tile):
+            // nothing is read or stored, the accumulator goes straight back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            continue;
+          }
+        }
 #pragma unroll 1
-        for (int b = 0; b < NBOX; ++b, ++cc) {
+        for (int b = 0; b < NBOX; ++b) {
           const int nc = tc.n0 + b * BOXC;           // first global column of the box
-          bool live = nc < N;
+          const bool live = nc < N;
           float bias_r[W];                            // independent of the accumulator: issued before the TMEM wait
 #pragma unroll
           for (int j = 0; j < W; j += 4) {
@@ -384,28 +394,40 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 const float am = __uint_as_float(__ldg(p.img_absmax + tc.z));
                 if (am > 0.f) aff_unscale = exp2f(2.0f * ceilf(log2f(am)));
               }
+              aff_rowsum = 0.f;
             }
             const float mx = aff_mx, rmx = aff_rmx, unscale = aff_unscale;
-            const uint8_t* cnt = (p.counts && m < M) ? p.counts + ((long long)tc.z * M + m) * M + n : nullptr;
+            const bool relu = p.threshold & 1, nodiv = p.threshold & 2;
+            // y / mx without the compiler's IEEE division subroutine: its range check sends zero and tiny numerators --
+            // most of a thresholded affinity -- down a ~100-instruction slow path (ncu: 84 % of this kernel's 617 M warp
+            // instructions). mx is the largest Gram diagonal: exactly 1 for most normalised images (nothing to do), else
+            // q = y r, one residual correction: q + (y - q mx) r -- the correctly rounded quotient for these operand
+            // ranges (0 <= y <= ~mx, mx in the normal range).
+            const bool scale = !nodiv && mx != 1.0f;
 #pragma unroll
             for (int e = 0; e < W; ++e) {
               float y = x[e];
-              if (p.threshold & 1) y = y > 0.f ? y : 0.f;   // W * (W > 0)
-              if (!(p.threshold & 2)) {                     // W / W.max()
-                // y / mx without the compiler's IEEE division subroutine: its range check sends zero and tiny numerators
-                // -- most of a thresholded affinity -- down a ~100-instruction slow path (ncu: 84 % of this kernel's
-                // 617 M warp instructions). mx is the largest Gram diagonal: exactly 1 for most normalised images
-                // (nothing to do), else q = y r, one residual correction: q + (y - q mx) r -- the correctly rounded
-                // quotient for these operand ranges (0 <= y <= ~mx, mx in the normal range).
-                if (mx != 1.0f) {
-                  const float q0 = y * rmx;
-                  y = fmaf(fmaf(-q0, mx, y), rmx, q0);
-                }
-              } else {
-                y *= unscale;
+              if (relu) y = fmaxf(y, 0.f);                  // W * (W > 0)
+              if (scale) {                                  // W / W.max()
+                const float q0 = y * rmx;
+                y = fmaf(fmaf(-q0, mx, y), rmx, q0);
               }
-              if (cnt && n + e < M) y += static_cast<float>(cnt[e]) * p.lambda;   // + W_color * lambda
-              x[e] = (n + e < M) ? y : 0.f;
+              if (nodiv) y *= unscale;
+              x[e] = y;
+            }
+            // edge boxes only (last tile row / column of the image): the colour term and the bounds are per element
+            const bool edge = nc + BOXC > M || tc.m0 + BM > M;   // (uniform)
+            const bool rowok = !edge || m < M;
+            if (p.counts != nullptr && rowok) {
+              const uint8_t* cnt = p.counts + ((long long)tc.z * M + m) * M + n;
+#pragma unroll
+              for (int e = 0; e < W; ++e)
+                if (!edge || n + e < M) x[e] += static_cast<float>(cnt[e]) * p.lambda;   // + W_color * lambda
+            }
+            if (edge) {
+#pragma unroll
+              for (int e = 0; e < W; ++e)
+                if (n + e >= M) x[e] = 0.f;
             }
             if (p.tri) {
               // ---- symmetric mode. The matrix is exactly symmetric by construction (the same value is written to
@@ -416,10 +438,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
               // two halves of the tile come out of differently ordered accumulations (the split-fp16 K groups are
               // swapped between the operands), so only the elements on or above the diagonal are stored -- each to
               // both positions -- and the TMA store is skipped: W[i, j] and W[j, i] are the same bits everywhere.
-              const bool upper = tc.m0 < tc.n0, diag = tc.m0 == tc.n0;
-              live = live && upper;                          // (the odd CTA's below-diagonal tile stores nothing at all)
-              const bool rowok = m < M;
-              if (b == 0) aff_rowsum = 0.f;
+              // (The odd CTA's below-diagonal tile never gets here.)
+              const bool upper = tc.m0 < tc.n0;
               float xm[W];
 #pragma unroll
               for (int e = 0; e < W; ++e) {
@@ -427,51 +447,52 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 aff_rowsum += xm[e];
               }
               float* part = p.deg_part + (long long)tc.z * (8 * tiles_n) * p.ld_part;
-              if (diag) {
-                float* Wz = reinterpret_cast<float*>(p.out) + (long long)tc.z * M * p.ldo;
+              float* Wz = reinterpret_cast<float*>(p.out) + (long long)tc.z * M * p.ldo;
+              if (b == NBOX - 1 && rowok)   // row partial slot of (column tile j, slice sl)
+                part[(long long)((tc.n0 / BN) * 4 + sl) * p.ld_part + m] = aff_rowsum;
+              if (!upper) {                 // diagonal tile: direct stores only, no staging / TMA store for this box
                 if (rowok) {
+                  float* rowp = Wz + (long long)m * p.ldo + n;      // (m, n + e)
+                  float* colp = Wz + (long long)n * p.ldo + m;      // (n + e, m)
 #pragma unroll
                   for (int e = 0; e < W; ++e) {
-                    if (n + e >= m && n + e < p.ldo) Wz[(long long)m * p.ldo + n + e] = x[e];       // on / above the diagonal
-                    if (n + e > m && n + e < M) Wz[(long long)(n + e) * p.ldo + m] = x[e];          // its mirror image
+                    if (n + e >= m && n + e < p.ldo) rowp[e] = x[e];                          // on / above the diagonal
+                    if (n + e > m && n + e < M) colp[(long long)e * p.ldo] = x[e];            // its mirror image
                   }
                 }
+                continue;
               }
-              if (upper) {
-                // mirrored store W[z, n + e, m] = W[z, m, n + e]: lanes hold consecutive m -> 128 B per warp store
-                float* Wz = reinterpret_cast<float*>(p.out) + (long long)tc.z * M * p.ldo;
-                if (m < p.ldo) {
+              // mirrored store W[z, n + e, m] = W[z, m, n + e]: lanes hold consecutive m -> 128 B per warp store
+              if (!edge || m < p.ldo) {
+                float* colp = Wz + (long long)n * p.ldo + m;
 #pragma unroll
-                  for (int e = 0; e < W; ++e)
-                    if (n + e < M) Wz[(long long)(n + e) * p.ldo + m] = xm[e];
-                }
-                // column sums over this warp's 32 rows: segmented butterfly (8 -> 4 -> 2 -> 1 values per lane)
-                float c4[4], c2[2], c1;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float mine = (lane & 16) ? xm[e + 4] : xm[e], theirs = (lane & 16) ? xm[e] : xm[e + 4];
-                  c4[e] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const float mine = (lane & 8) ? c4[e + 2] : c4[e], theirs = (lane & 8) ? c4[e] : c4[e + 2];
-                  c2[e] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
-                }
-                {
-                  const float mine = (lane & 4) ? c2[1] : c2[0], theirs = (lane & 4) ? c2[0] : c2[1];
-                  c1 = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
-                }
-                c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
-                c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
-                // lane l now holds the sum of column e = 4 * bit4 + 2 * bit3 + bit2 of l (all four lanes l & 3 agree)
-                if ((lane & 3) == 0) {
-                  const int e = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                  // column partial slot of (row tile i = m0 / BM, lane quarter q); it belongs to matrix row n + e
-                  part[(long long)(4 * tiles_n + (tc.m0 / BM) * 4 + q) * p.ld_part + n + e] = c1;
-                }
+                for (int e = 0; e < W; ++e)
+                  if (!edge || n + e < M) colp[(long long)e * p.ldo] = xm[e];
               }
-              if (b == NBOX - 1 && tc.m0 <= tc.n0 && rowok)   // row partial slot of (column tile j, slice sl)
-                part[(long long)((tc.n0 / BN) * 4 + sl) * p.ld_part + m] = aff_rowsum;
+              // column sums over this warp's 32 rows: segmented butterfly (8 -> 4 -> 2 -> 1 values per lane)
+              float c4[4], c2[2], c1;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float mine = (lane & 16) ? xm[e + 4] : xm[e], theirs = (lane & 16) ? xm[e] : xm[e + 4];
+                c4[e] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+              }
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float mine = (lane & 8) ? c4[e + 2] : c4[e], theirs = (lane & 8) ? c4[e] : c4[e + 2];
+                c2[e] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+              }
+              {
+                const float mine = (lane & 4) ? c2[1] : c2[0], theirs = (lane & 4) ? c2[0] : c2[1];
+                c1 = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+              }
+              c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+              c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
+              // lane l now holds the sum of column e = 4 * bit4 + 2 * bit3 + bit2 of l (all four lanes l & 3 agree)
+              if ((lane & 3) == 0) {
+                const int e = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                // column partial slot of (row tile i = m0 / BM, lane quarter q); it belongs to matrix row n + e
+                part[(long long)(4 * tiles_n + (tc.m0 / BM) * 4 + q) * p.ld_part + n + e] = c1;
+              }
             }
           }
           // the staging box is free once the store issued two boxes ago has finished READING it
@@ -507,6 +528,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
             tma_store_commit();
           }
+          ++cc;   // (boxes that skip the staging buffers -- diagonal affinity tiles -- do not advance the buffer parity)
         }
       }
       if (issuer) tma_store_wait_all<0>();

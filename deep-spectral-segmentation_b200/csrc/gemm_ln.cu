@@ -266,17 +266,20 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       __syncwarp();
     };
     auto write_panel = [&](int m0, int par, int li) {
-      // slab k = columns [64 k, 64 k + 64): per instruction the warp covers two rows x 256 contiguous bytes
+      // slab k = columns [64 k, 64 k + 64): per instruction the warp covers two rows x 256 contiguous bytes. The loads
+      // of slab k + 1 (second read of x: L2) are issued before slab k is normalised, so the L2 latency of the six
+      // slabs overlaps the arithmetic instead of adding up (the producers' latency chain per block was longer than
+      // the six n-tiles of the qkv layer take on the tensor cores)
       const int c4 = lane & 15, rsel = lane >> 4;
-#pragma unroll 1
-      for (int k = 0; k < LG_SLABS; ++k) {
-        float4 xv[8];
+      auto load_slab = [&](int k, float4 (&xv)[8]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {   // issue the loads before waiting for the slab (second read of x: L2)
+        for (int i = 0; i < 8; ++i) {
           const int m = m0 + w * 16 + 2 * i + rsel;
           xv[i] = m < p.M ? __ldg(reinterpret_cast<const float4*>(p.x + (long long)m * LG_K + k * 64) + c4)
                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      };
+      auto put_slab = [&](int k, const float4 (&xv)[8]) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + k * 64 + c4 * 4));   // 3 KB, L1 resident
         const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + k * 64 + c4 * 4));
         if (li > 0) mbar_wait(a_free(k), (li - 1) & 1);   // the previous block's MMAs have read slab k
@@ -293,6 +296,15 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full(k));
+      };
+      float4 xa[8], xb[8];
+      load_slab(0, xa);
+#pragma unroll
+      for (int k = 0; k < LG_SLABS; k += 2) {
+        load_slab(k + 1, xb);
+        put_slab(k, xa);
+        if (k + 2 < LG_SLABS) load_slab(k + 2, xa);
+        put_slab(k + 1, xb);
       }
     };
     int li = 0;
