@@ -89,7 +89,10 @@ constexpr int FA_NBARS = 8 + 2 * FA_KV_STAGES + 10;
 template <int ABL>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO, int T, int heads,
-                         int nq2, int total_items) {
+                         int nq2, int total_items, int flags) {
+  // flags (tuning switches, both on by default): 1 = rotate the query-pair index over the items, 2 = take the exponentials
+  // of tiles j > 0 against the reference maximum of the earlier tiles (no separate row-maximum pass)
+  const bool f_rotate = flags & 1, f_lazy = flags & 2;
   extern __shared__ __align__(1024) uint8_t fa_smem[];
   __shared__ __align__(8) uint64_t bars[FA_NBARS];
   __shared__ uint32_t tmem_ptr_s;
@@ -159,7 +162,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
       // with the plain w % nq2 a CTA (w = blockIdx + k * 148, 148 % 4 == 0) would get the SAME pair index in every item,
       // and the CTAs that only ever see the light last pair (a 5-row tail tile at T = 901) idle at the end of the
       // kernel while the others are still on full pairs (ncu: 8.5 % of the stall samples on EXIT)
-      const int bh = w / nq2, qp = (w % nq2 + bh) % nq2;
+      const int bh = w / nq2, qp = f_rotate ? (w % nq2 + bh) % nq2 : w % nq2;
       const int h = bh % heads, row0 = (bh / heads) * T;   // first row of this image in the [B*T, 3d] matrix
       const int qb = qi & 1;
       const uint32_t qph = (qi >> 1) & 1;
@@ -265,7 +268,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
       // with the plain w % nq2 a CTA (w = blockIdx + k * 148, 148 % 4 == 0) would get the SAME pair index in every item,
       // and the CTAs that only ever see the light last pair (a 5-row tail tile at T = 901) idle at the end of the
       // kernel while the others are still on full pairs (ncu: 8.5 % of the stall samples on EXIT)
-      const int bh = w / nq2, qp = (w % nq2 + bh) % nq2;
+      const int bh = w / nq2, qp = f_rotate ? (w % nq2 + bh) % nq2 : w % nq2;
       const int h = bh % heads;
       const int q0 = (2 * qp + g) * FA_BM;
       const bool dead = q0 >= T || ((ABL & 64) && g == 1);   // odd number of query tiles: nothing to do for B in the last pair
@@ -326,16 +329,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
             if (!(ABL & 2)) tmem_st_32x16(p_col + c * 16, pk);
             else rs2[0] += pk[0] ^ pk[5] ^ pk[10] ^ pk[15];   // keep the values alive
           };
-          if (j == 0) {
-            // ---- first key tile of the item: no reference maximum yet, so the row maximum comes first
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (c * 32 < kc) tmem_ld_32x32(s_col + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&v[c * 32]));
-            tmem_ld_wait();
-            FA_TRACE(tb + 1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free(g));   // S_g is in registers: the next score tile may overwrite it
+          for (int c = 0; c < 4; ++c)
+            if (c * 32 < kc) tmem_ld_32x32(s_col + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&v[c * 32]));
+          tmem_ld_wait();
+          FA_TRACE(tb + 1);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free(g));   // S_g is in registers: the next score tile may overwrite it
+          if (j == 0 || !f_lazy) {
+            // ---- the row maximum first (always for the first key tile of an item: there is no reference yet)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               if (c * 32 < kc) {
@@ -346,8 +349,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
                 }
               }
             }
-            m_ref = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
+            const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
             FA_TRACE(tb + 2);
+            if (j > 0) {
+              // P_g is single buffered and O_g accumulates in place: P_g V_{j-1} must be complete (issued long ago)
+              mbar_wait(o_full(g), (m - 1) & 1);
+              tc_fence_after();
+              const bool raise = (mx - m_ref) * sc > FA_RESCALE_LOG2;
+              if (__any_sync(0xffffffffu, raise)) {   // rare: rescale this warp's rows of O_g in TMEM
+                const float f = raise ? ex2_approx((m_ref - mx) * sc) : 1.0f;
+                uint32_t t[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  tmem_ld_32x32(o_col + c * 32, t);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
+                  tmem_st_32x32(o_col + c * 32, t);
+                }
+                tmem_st_wait();
+                l_run *= f;
+                if (raise) m_ref = mx;
+              }
+            } else {
+              m_ref = mx;
+            }
             FA_TRACE(tb + 3);
             const float msc = m_ref * sc;
 #pragma unroll
@@ -356,35 +382,23 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
                 chunk(c, msc, false);
                 // release tile B's first key tile when tile A is half way through its first exponentials: the two
                 // groups then stay about half a period apart (one in its MUFU phase, the other loading / reducing)
-                if (c == 1 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+                if (c == 1 && j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
               }
             }
-            if (kc <= 32 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // (short first tile)
+            if (kc <= 32 && j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // (short first tile)
           } else {
             // ---- later key tiles: exponentials are taken relative to the reference maximum of the EARLIER tiles right
-            // away (softmax is shift invariant; fp16 P and the fp32 sums have 2^8 of headroom), chunk 0 while the TMEM
-            // loads of chunks 1-3 are still in flight; only if this tile turns out to exceed the reference by more than
+            // away (softmax is shift invariant; fp16 P and the fp32 sums have 2^8 of headroom) with the row maximum
+            // tracked alongside (FMNMX3, ALU pipe); only if this tile turns out to exceed the reference by more than
             // 2^8 is the reference raised and the tile redone (rare).
-            tmem_ld_32x32(s_col, *reinterpret_cast<uint32_t (*)[32]>(&v[0]));
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 1; c < 4; ++c)
-              if (c * 32 < kc) tmem_ld_32x32(s_col + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&v[c * 32]));
-            FA_TRACE(tb + 1);
-            // P_g is single buffered and O_g accumulates in place: P_g V_{j-1} must be complete (issued long ago)
-            mbar_wait(o_full(g), (m - 1) & 1);
+            mbar_wait(o_full(g), (m - 1) & 1);   // P_g is single buffered: P_g V_{j-1} must be complete
             tc_fence_after();
             FA_TRACE(tb + 2);
             float msc = m_ref * sc;
-            chunk(0, msc, true);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free(g));   // S_g is in registers: the next score tile may overwrite it
-            FA_TRACE(tb + 3);
 #pragma unroll
-            for (int c = 1; c < 4; ++c)
+            for (int c = 0; c < 4; ++c)
               if (c * 32 < kc) chunk(c, msc, true);
+            FA_TRACE(tb + 3);
             const float mx = fmaxf(fmaxf(mxc[0], mxc[1]), fmaxf(mxc[2], mxc[3]));
             const bool raise = (mx - m_ref) * sc > FA_RESCALE_LOG2;
             if (__any_sync(0xffffffffu, raise)) {   // rare: rescale this warp's rows of O_g in TMEM, redo the tile
@@ -478,8 +492,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
 
 int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cudaStream_t st) {
   DSS_REQUIRE(B > 0 && T > 0 && heads > 0, "attention: empty problem");
+  static int flags = 3;
   static int abl = -1;
   if (abl < 0) {
+    if (const char* e = getenv("DSS_ATTN_FLAGS")) flags = atoi(e);   // tuning: bit 0 item rotation, bit 1 lazy reference
     const char* e = getenv("DSS_ATTN_ABL");   // tuning only
     abl = e ? atoi(e) : 0;
     DSS_CHECK_CUDA(cudaFuncSetAttribute(attention_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
@@ -510,10 +526,10 @@ int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cud
     DSS_CHECK_CUDA(cudaMemset(trace_dev, 0, 16384 * sizeof(long long)));
     DSS_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace, &trace_dev, sizeof(trace_dev)));
   }
-#define DSS_ABL_CASE(n) case n: attention_tcgen05_kernel<n><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total); break;
+#define DSS_ABL_CASE(n) case n: attention_tcgen05_kernel<n><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total, flags); break;
   switch (abl) {
     DSS_ABL_CASE(1) DSS_ABL_CASE(2) DSS_ABL_CASE(4) DSS_ABL_CASE(8) DSS_ABL_CASE(16) DSS_ABL_CASE(32) DSS_ABL_CASE(3) DSS_ABL_CASE(7) DSS_ABL_CASE(39) DSS_ABL_CASE(24) DSS_ABL_CASE(63) DSS_ABL_CASE(64) DSS_ABL_CASE(65) DSS_ABL_CASE(127) DSS_ABL_CASE(88) DSS_ABL_CASE(256) DSS_ABL_CASE(512) DSS_ABL_CASE(768) DSS_ABL_CASE(1024)
-    default: attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total);
+    default: attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total, flags);
   }
   if (trace_path) {
     static long long host[16384];
@@ -523,7 +539,7 @@ int launch_attention_tc(const void* qkv, void* out, int B, int T, int heads, cud
     if (f) { fwrite(host, sizeof(host), 1, f); fclose(f); }
   }
 #else
-  attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total);
+  attention_tcgen05_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(tm, tmO, T, heads, nq2, total, flags);
 #endif
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;

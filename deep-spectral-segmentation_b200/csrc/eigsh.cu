@@ -95,7 +95,7 @@ __device__ __forceinline__ int sturm_count(const double* alpha, const double* be
 }
 
 __host__ __device__ inline size_t eig_double_bytes(int mmax) {
-  size_t nd = (size_t)3 * mmax + 2 * EIG_MAX_K + EIG_WARPS;
+  size_t nd = (size_t)3 * mmax + 2 * (EIG_MAX_K + 1) + EIG_WARPS;
   nd = (nd + 1) & ~(size_t)1;
   return nd * sizeof(double);
 }
@@ -115,9 +115,9 @@ lanczos_laplacian_kernel(EigParams p) {
   double* alpha = reinterpret_cast<double*>(smem_raw);      // [mmax]
   double* beta = alpha + mmax;                               // [mmax]   beta[j] = ||w_j|| (couples j, j+1)
   double* beta2 = beta + mmax;                               // [mmax]
-  double* theta = beta2 + mmax;                              // [EIG_MAX_K]
-  double* red = theta + EIG_MAX_K;                           // [EIG_WARPS]
-  double* resid_s = red + EIG_WARPS;                         // [EIG_MAX_K]
+  double* theta = beta2 + mmax;                              // [EIG_MAX_K + 1] (the wanted pairs + the guard pair)
+  double* red = theta + EIG_MAX_K + 1;                       // [EIG_WARPS]
+  double* resid_s = red + EIG_WARPS;                         // [EIG_MAX_K + 1]
   // float arrays start 16-byte aligned (float4 access): the double block is padded to an even count
   float* xs = reinterpret_cast<float*>(smem_raw + eig_double_bytes(mmax));  // [Npad] scaled mat-vec input
   float* wv = xs + Npad;                                     // [Npad] working vector
@@ -132,8 +132,8 @@ lanczos_laplacian_kernel(EigParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* basis = p.basis + (size_t)blockIdx.x * (size_t)(mmax + 1) * Npad;
-  double* triS = p.tri + (size_t)blockIdx.x * 2 * (size_t)(Kw > 0 ? Kw : 1) * mmax;  // [Kw][mmax] Ritz vectors of T
-  double* triB = triS + (size_t)(Kw > 0 ? Kw : 1) * mmax;                             // [Kw][mmax] temp
+  double* triS = p.tri + (size_t)blockIdx.x * 2 * (size_t)(Kw + 1) * mmax;  // [Kw + 1][mmax] Ritz vectors of T
+  double* triB = triS + (size_t)(Kw + 1) * mmax;                            // [Kw + 1][mmax] temp
 
   for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
     const float* W = p.W + (size_t)img * N * ldw;
@@ -378,6 +378,11 @@ lanczos_laplacian_kernel(EigParams p) {
         const int every = (n <= 64) ? 4 : 8;
         const bool check = breakdown || n == mmax || n >= N - 1 || (n >= n0 && ((n - n0) % every) == 0);
         const int kk = min(Kw, n);  // Ritz pairs that exist
+        // + one GUARD pair (the next Ritz value): the wanted pairs having small residuals does not exclude an eigenvalue
+        // of a tight cluster that has not emerged from the Krylov space yet; such an eigenvalue shows up as a poorly
+        // converged next Ritz value whose residual interval reaches into the wanted range (found with K = 32 on a
+        // spectrum with 1e-4 gaps: 81 steps, all residuals < tol, eigenvalue 32 off by 5e-3)
+        const int kg = min(Kw + 1, n);
         if (check) {
           // Gershgorin bounds (every warp computes them redundantly: n <= mmax small)
           double gl = 1e300, gh = -1e300;
@@ -393,7 +398,7 @@ lanczos_laplacian_kernel(EigParams p) {
           }
           const double span = fmax(gh - gl, 1e-30);
           gl -= 1e-3 * span; gh += 1e-3 * span;
-          for (int k = warp; k < kk; k += EIG_WARPS) {
+          for (int k = warp; k < kg; k += EIG_WARPS) {
             // k-th largest eigenvalue = ascending index t = n-1-k ; lambda_t >= x  <=>  count(x) <= t
             const int t = n - 1 - k;
             double lo = gl, hi = gh;
@@ -469,6 +474,8 @@ lanczos_laplacian_kernel(EigParams p) {
             int ok = 1;
             for (int k = 0; k < kk; ++k) ok &= (resid_s[k] <= (double)p.tol * anorm);
             ok &= (kk == Kw);
+            if (kg > Kw && Kw > 0 && !breakdown && n < N - 1)   // guard: nothing hidden above the last wanted Ritz value
+              ok &= (theta[Kw] + resid_s[Kw] <= theta[Kw - 1] + (double)p.tol * anorm);
             s_flag = ok;
           }
           __syncthreads();
@@ -575,7 +582,7 @@ extern "C" size_t dss_eigsh_workspace_bytes(int B, int N, int K, int max_steps) 
   const int mmax = eig_resolve(N, K, max_steps);
   const int grid = eig_grid(B, Npad, mmax);
   const size_t basis = align_up((size_t)grid * (mmax + 1) * Npad * sizeof(float), 256);
-  const size_t tri = align_up((size_t)grid * 2 * K * mmax * sizeof(double), 256);
+  const size_t tri = align_up((size_t)grid * 2 * (K + 1) * mmax * sizeof(double), 256);
   return basis + tri;
 }
 
