@@ -40,7 +40,7 @@ def parse():
                     help="c2 = configs[1] (the metric's config, default); c3 = dino_vitb8 480px colour-KNN K=15; "
                          "c4 = VOC-shaped variable sizes, dino_vits16 K=5; c5 = dino_vitb8 640px K=32 + N sweep")
     ap.add_argument("--images-per-step", type=int, default=0,
-                    help="per GPU; 0 = workload default (c2: 296 = 2 x 148 SMs, c3: 16, c4: 592, c5: 4)")
+                    help="per GPU; 0 = workload default (c2: 296 = 2 x 148 SMs, c3: 148, c4: 592, c5: 148)")
     ap.add_argument("--size", type=int, default=480)
     ap.add_argument("--K", type=int, default=5)
     ap.add_argument("--model", default="dino_vits16")
@@ -653,12 +653,14 @@ def run_c3(ctx: Ctx):
     import numpy as np
     model_name, S, K, lam = "dino_vitb8", 480, 15, 10.0
     sd = ctx.weights(model_name)
-    B = args.images_per_step or 16
+    B = args.images_per_step or 148      # one eigensolver CTA per SM
+    vb = 16                              # ViT launch sequence per 16 images (61 MB of workspace per image at T = 3601)
     model = ctx.vit.DinoViT(model_name, sd, device=dev)
     P, d, depth = model.patch_size, model.dim, model.depth
     Hp = S // P
     N = Hp * Hp
-    host_imgs = ctx.synth.blobs_batch(B, S, S, seed0=ctx.rank * B)
+    base = ctx.synth.blobs_batch(min(B, 16), S, S, seed0=ctx.rank * 16)     # 16 distinct images, tiled to the step size
+    host_imgs = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous()
     lr_u8 = _color_inputs(ctx, host_imgs, Hp, Hp)
     host_rgb = torch.from_numpy((lr_u8 / 255.0).reshape(B, N, 3).astype(np.float32)).pin_memory()
     host_imgs = host_imgs.pin_memory()
@@ -669,7 +671,8 @@ def run_c3(ctx: Ctx):
     last = {}
 
     def step(imgs=dev_imgs, rgb=dev_rgb):
-        model.forward_k(imgs, out=feats)
+        for s_ in range(0, B, vb):
+            model.forward_k(imgs[s_:s_ + vb], out=feats[s_:s_ + vb])
         cc = ctx.spectral.knn_color_counts(rgb, Hp, Hp)
         ctx.spectral.affinity(feats, True, True, cc, lam, out=Wm, degree=deg)
         last["out"] = ctx.spectral.eigsh_laplacian(Wm, N, K, degree=deg)
@@ -814,7 +817,7 @@ def run_c5(ctx: Ctx):
     import numpy as np
     model_name, K = "dino_vitb8", 32
     sd = ctx.weights(model_name)
-    B = args.images_per_step or 4
+    B = args.images_per_step or 148      # one eigensolver CTA per SM
     model = ctx.vit.DinoViT(model_name, sd, device=dev)
     P, d, depth = model.patch_size, model.dim, model.depth
     W, steps = max(args.warmup, 3), args.steps
@@ -824,7 +827,7 @@ def run_c5(ctx: Ctx):
     for S in (240, 320, 480, 640):
         Hp = S // P
         N = Hp * Hp
-        nb = B if S == 640 else max(B, min(64, 23040 // max(1, N // 100)))    # more images at small N (fills the GPU)
+        nb = B
         host_imgs = ctx.synth.blobs_batch(min(nb, 8), S, S, seed0=7 + ctx.rank)
         host_imgs = host_imgs.repeat((nb + 7) // 8, 1, 1, 1)[:nb].contiguous().pin_memory()
         dev_imgs = host_imgs.to(dev)
