@@ -440,9 +440,12 @@ def vit_alg(P, d, depth_full, N, n_images):
     return {
         "gemm_patch": ("tensor", 2.0 * n_images * N * (3 * P * P) * d),
         "gemm_qkv": ("tensor", L * 2.0 * M * d * 3 * d),
-        "gemm_proj": ("tensor", L * 2.0 * M * d * d),
+        # proj / fc2 add into the fp32 residual stream: A read (f16) + x read-modify-write (TMA reduce-add at the L2) are
+        # compulsory HBM bytes; at 77 / 192 FLOP per byte their HBM time exceeds their tensor time,
+        # so the roofline that bounds them is the copy bandwidth
+        "gemm_proj": ("hbm", L * M * (d * 2.0 + d * 8.0)),
         "gemm_fc1": ("tensor", L * 2.0 * M * d * hid),
-        "gemm_fc2": ("tensor", L * 2.0 * M * hid * d),
+        "gemm_fc2": ("hbm", L * M * (hid * 2.0 + d * 8.0)),
         "gemm_kproj": ("tensor", 2.0 * M * d * d),
         "attention": ("tensor", L * 4.0 * n_images * (d // 64) * T * T * 64),
         "layernorm": ("hbm", (2 * L + 1) * M * d * (4 + 2)),

@@ -74,6 +74,7 @@ struct dss_vit {
   std::vector<dss::BlockW> blocks;
   std::vector<float> pos_host;                        // [1 + grid0^2, d] fp32 host copy
   std::map<std::pair<int, int>, float*> pos_cache;    // (Hp, Wp) -> device [T, d]
+  std::vector<std::pair<int, int>> pos_order;         // insertion order: the cache is bounded (oldest grid evicted)
 };
 
 namespace dss {
@@ -144,7 +145,20 @@ static int get_pos(dss_vit* h, int Hp, int Wp, cudaStream_t st, float** out) {
   DSS_CHECK_CUDA(cudaMalloc(&dev, (size_t)T * d * sizeof(float)));
   DSS_CHECK_CUDA(cudaMemcpyAsync(dev, pos.data(), (size_t)T * d * sizeof(float), cudaMemcpyHostToDevice, st));
   DSS_CHECK_CUDA(cudaStreamSynchronize(st));  // `pos` is a pageable temporary
+  // bounded: data sets with hundreds of distinct image sizes must not grow the cache without limit. Eviction happens
+  // after the stream synchronisation above, so no kernel that was given the evicted pointer is still running.
+  constexpr size_t kMaxPosGrids = 64;
+  if (h->pos_order.size() >= kMaxPosGrids) {
+    auto old = h->pos_order.front();
+    h->pos_order.erase(h->pos_order.begin());
+    auto oit = h->pos_cache.find(old);
+    if (oit != h->pos_cache.end()) {
+      cudaFree(oit->second);
+      h->pos_cache.erase(oit);
+    }
+  }
   h->pos_cache[key] = dev;
+  h->pos_order.push_back(key);
   *out = dev;
   return DSS_OK;
 }
@@ -394,6 +408,7 @@ extern "C" int dss_vit_load_weights(dss_vit_t* h, const dss_vit_weights* w, dss_
   DSS_CHECK_CUDA(cudaStreamSynchronize(st));
   for (auto& kv : h->pos_cache) cudaFree(kv.second);
   h->pos_cache.clear();
+  h->pos_order.clear();
   h->loaded = true;
   return DSS_OK;
 }

@@ -544,15 +544,16 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
             tm["wait_gpu"] += tb - ta
             tm["submit"] += time.perf_counter() - tb
 
-        def flush(key, items):
-            """First half of a batch: stage, copy, enqueue every kernel and the read-back copies; then finish the
-            PREVIOUS batch while this one runs."""
+        def flush(key, group):
+            """First half of a batch: wait for its staging copies, start the H2D copy, enqueue every kernel and the
+            read-back copies; then finish the PREVIOUS batch while this one runs."""
             H, W = key
             ta = time.perf_counter()
-            ring = rings.get(key)
-            if ring is None:
-                ring = rings[key] = io_pipeline.PinnedRing(key, max(1, int(batch_size)), dev)
-            slot, host = ring.stage([it[0] for it in items])
+            ring, slot, items = rings[key], group["slot"], group["items"]
+            for f in group["futures"]:
+                if f is not None:
+                    f.result()
+            host = ring.bufs[slot][:len(items)]
             tb = time.perf_counter()
             k = model.forward_k(ring.to_device(slot, host), which_block=which_block)
             Hp, Wp = H // patch_size, W // patch_size
@@ -597,7 +598,6 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
             while len(in_flight) > 1:
                 finish(in_flight.pop(0))
 
-        batcher = _Batcher(batch_size, flush)
         todo = []
         for i in range(len(dataset)):
             file = dataset.filenames[i]
@@ -605,9 +605,38 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
                 print(f"Skipping existing file {str(Path(eigs_dir) / (file[:-4] + '.pth'))}")
             else:
                 todo.append(i)
-        for image, file, index in io_pipeline.ImagePrefetcher(dataset.__getitem__, todo, num_workers):
-            batcher.add((int(image.shape[0]), int(image.shape[1])), (image, file, index))
-        batcher.finish()
+        # Images are grouped by shape. As soon as a decoded image arrives it is given a row of its group's page-locked
+        # batch and the copy into it runs on the staging pool (GIL-free) while this thread keeps pulling images; a group
+        # is flushed when it is full, or early (largest first) when too many images are waiting.
+        cap = max(1, int(batch_size))
+        groups: Dict[tuple, dict] = {}
+        pending = 0
+
+        def flush_group(key):
+            nonlocal pending
+            group = groups.pop(key)
+            pending -= len(group["items"])
+            flush(key, group)
+
+        for image, file, index in io_pipeline.ImagePrefetcher(dataset.__getitem__, todo, num_workers, lookahead=cap):
+            key = (int(image.shape[0]), int(image.shape[1]))
+            ring = rings.get(key)
+            if ring is None:
+                # page-locked memory per shape: 3 batches. Data sets with very many distinct sizes get small batches for
+                # the sizes that turn up late (bounded host memory; the common sizes come first in practice)
+                ring = rings[key] = io_pipeline.PinnedRing(key, cap if len(rings) < 12 else min(cap, 8), dev, slots=3)
+            group = groups.get(key)
+            if group is None:
+                group = groups[key] = {"slot": ring.begin(), "items": [], "futures": []}
+            group["futures"].append(ring.copy_async(group["slot"], len(group["items"]), image))
+            group["items"].append((None, file, index))   # (the pixels now live in the page-locked batch)
+            pending += 1
+            if len(group["items"]) >= ring.capacity:
+                flush_group(key)
+            elif pending > 8 * cap:
+                flush_group(max(groups, key=lambda k_: len(groups[k_]["items"])))
+        for key in list(groups.keys()):
+            flush_group(key)
         while in_flight:
             finish(in_flight.pop(0))
     seconds = time.perf_counter() - t_start

@@ -70,6 +70,7 @@ class PinnedRing:
     def __init__(self, shape: Tuple[int, int], capacity: int, device, slots: int = 2, copy_threads: int = 6):
         H, W = shape
         self.device = device
+        self.capacity = capacity
         # torch.empty(pin_memory=True) allocates page-locked memory directly (no pageable copy first)
         self.bufs = [torch.empty(capacity, H, W, 3, dtype=torch.uint8, pin_memory=True) for _ in range(slots)]
         self.np_bufs = [b.numpy() for b in self.bufs]    # views of the page-locked memory
@@ -99,6 +100,23 @@ class PinnedRing:
                     np.copyto(dst[j], images[j].numpy())
             list(self._pool.map(part, range(n)))
         return slot, buf
+
+    # ---- incremental staging: the caller assigns (slot, row) as images arrive and the copies run on the pool while it
+    # keeps pulling decoded images; the batch is complete when its futures are
+    def begin(self) -> int:
+        slot = self.next
+        self.next = (self.next + 1) % len(self.bufs)
+        if self.events[slot] is not None:
+            self.events[slot].synchronize()
+        return slot
+
+    def copy_async(self, slot: int, j: int, image: torch.Tensor):
+        import numpy as np
+        dst, src = self.np_bufs[slot][j], image.numpy()
+        if self._pool is None:
+            np.copyto(dst, src)
+            return None
+        return self._pool.submit(np.copyto, dst, src)
 
     def to_device(self, slot: int, host_batch: torch.Tensor) -> torch.Tensor:
         dev = host_batch.to(self.device, non_blocking=True)
