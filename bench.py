@@ -401,7 +401,12 @@ class Ctx:
         for name, (n_l, t_ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
             ent = {"kernel": name, "launches": n_l, "total_ms": round(t_ms, 4), "share": round(t_ms / total_ms, 4)}
             if name in alg and n_l:
-                bound, work = alg[name]          # work = algorithmic FLOPs / bytes summed over the class's launches of ONE step
+                if alg[name][0] == "auto":
+                    _, fl, by = alg[name]
+                    bound, work = ("hbm", by) if by / (self.peaks["hbm_gbs"] * 1e9) > fl / (self.peaks["tflops_sustained"] * 1e12) \
+                        else ("tensor", fl)
+                else:
+                    bound, work = alg[name]      # work = algorithmic FLOPs / bytes summed over the class's launches of ONE step
                 per_launch_s = t_ms / n_l * 1e-3
                 launches_per_step = n_l / max(1, self._prof_steps)
                 ach = work / launches_per_step / per_launch_s
@@ -443,9 +448,10 @@ def vit_alg(P, d, depth_full, N, n_images):
         # proj / fc2 add into the fp32 residual stream: A read (f16) + x read-modify-write (TMA reduce-add at the L2) are
         # compulsory HBM bytes; at 77 / 192 FLOP per byte their HBM time exceeds their tensor time,
         # so the roofline that bounds them is the copy bandwidth
-        "gemm_proj": ("hbm", L * M * (d * 2.0 + d * 8.0)),
+        # ("auto", flops, bytes): whichever of the two takes longer at the measured peaks is the roofline that binds
+        "gemm_proj": ("auto", L * 2.0 * M * d * d, L * M * (d * 2.0 + d * 8.0)),
         "gemm_fc1": ("tensor", L * 2.0 * M * d * hid),
-        "gemm_fc2": ("hbm", L * M * (hid * 2.0 + d * 8.0)),
+        "gemm_fc2": ("auto", L * 2.0 * M * hid * d, L * M * (hid * 2.0 + d * 8.0)),
         "gemm_kproj": ("tensor", 2.0 * M * d * d),
         "attention": ("tensor", L * 4.0 * n_images * (d // 64) * T * T * 64),
         "layernorm": ("hbm", (2 * L + 1) * M * d * (4 + 2)),
@@ -790,8 +796,9 @@ def run_c4(ctx: Ctx):
     for (H, Wd), cnt in groups.items():
         N = (H // P) * (Wd // P)
         m_steps = float(infos[(H, Wd)][:, 0].float().mean().item())
-        for k_, (bound, work) in {**vit_alg(P, d, depth - 1, N, cnt), **eig_alg(cnt, N, d, K, m_steps)}.items():
-            alg[k_] = (bound, alg.get(k_, (bound, 0.0))[1] + work)
+        for k_, ent in {**vit_alg(P, d, depth - 1, N, cnt), **eig_alg(cnt, N, d, K, m_steps)}.items():
+            prev = alg.get(k_, (ent[0],) + (0.0,) * (len(ent) - 1))
+            alg[k_] = (ent[0],) + tuple(a + b for a, b in zip(prev[1:], ent[1:]))
     kernels = ctx.kernel_table(prof, alg)
     conv = sum(int(v[:, 1].sum().item()) for v in infos.values())
     line = {"metric": "images/sec (features+eigs, VOC-shaped sizes, dino_vits16 K=5)", "value": ctx.world * B * steps / (ms * 1e-3),

@@ -282,16 +282,24 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       auto put_slab = [&](int k, const float4 (&xv)[8]) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + k * 64 + c4 * 4));   // 3 KB, L1 resident
         const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + k * 64 + c4 * 4));
-        if (li > 0) mbar_wait(a_free(k), (li - 1) & 1);   // the previous block's MMAs have read slab k
+        // normalise BEFORE waiting for the slab: what remains on the critical path between "the previous block's MMAs
+        // have read slab k" and "slab k of this block is in place" is 8 shared-memory stores, the proxy fence and the
+        // arrive (the MMA warp spent 29 % of its time waiting here when the arithmetic came after the wait)
+        uint32_t lo[8], hi[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = w * 16 + 2 * i + rsel;
           const float mean = s_mean[par * LG_BM + r], rstd = s_rstd[par * LG_BM + r];
-          const uint32_t lo = pack_half2((xv[i].x - mean) * rstd * g.x + bt.x, (xv[i].y - mean) * rstd * g.y + bt.y);
-          const uint32_t hi = pack_half2((xv[i].z - mean) * rstd * g.z + bt.z, (xv[i].w - mean) * rstd * g.w + bt.w);
+          lo[i] = pack_half2((xv[i].x - mean) * rstd * g.x + bt.x, (xv[i].y - mean) * rstd * g.y + bt.y);
+          hi[i] = pack_half2((xv[i].z - mean) * rstd * g.z + bt.z, (xv[i].w - mean) * rstd * g.w + bt.w);
+        }
+        if (li > 0) mbar_wait(a_free(k), (li - 1) & 1);   // the previous block's MMAs have read slab k
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = w * 16 + 2 * i + rsel;
           // 8 bytes at column 4 c4 of row r: 16-byte chunk c4 / 2 (XOR-swizzled with the row), half c4 & 1
           const uint32_t addr = sA + k * LG_SLAB_BYTES + r * 128 + ((((c4 >> 1) ^ (r & 7))) << 4) + ((c4 & 1) << 3);
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo[i]), "r"(hi[i]) : "memory");
         }
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
