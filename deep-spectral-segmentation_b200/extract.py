@@ -500,18 +500,18 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
                                               random_init=random_init)
     filenames = Path(images_list).read_text().splitlines()
     dataset = utils.ImagesDataset(filenames=filenames, images_root=images_root)
-    rings: Dict[tuple, io_pipeline.PinnedRing] = {}
     all_failed: List[str] = []
     import time
     t_start = time.perf_counter()   # model set-up (weights, packing) is done: what follows is the per-image pipeline
 
-    tm = {"stage": 0.0, "launch": 0.0, "wait_gpu": 0.0, "submit": 0.0}
+    tm = {"decode_wait": 0.0, "pinned_alloc": 0.0, "launch": 0.0, "wait_gpu": 0.0, "submit": 0.0}
     in_flight: List[dict] = []       # batches whose kernels / read-back copies are still running (software pipeline)
     with wr, _png_writer_pool(2) as png_pool:
         def finish(h):
             """Second half of a batch: wait for its read-back, retry stragglers, hand everything to the writers."""
             ta = time.perf_counter()
             h["event"].synchronize()
+            assembler.release(h["batch"])     # its host->device copy is long done: the decode threads may refill it
             tb = time.perf_counter()
             items, H, W, Hp, Wp = h["items"], h["H"], h["W"], h["Hp"], h["Wp"]
             evals, evecs, info = h["evals"], h["evecs"], h["info"]
@@ -544,18 +544,14 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
             tm["wait_gpu"] += tb - ta
             tm["submit"] += time.perf_counter() - tb
 
-        def flush(key, group):
-            """First half of a batch: wait for its staging copies, start the H2D copy, enqueue every kernel and the
-            read-back copies; then finish the PREVIOUS batch while this one runs."""
-            H, W = key
-            ta = time.perf_counter()
-            ring, slot, items = rings[key], group["slot"], group["items"]
-            for f in group["futures"]:
-                if f is not None:
-                    f.result()
-            host = ring.bufs[slot][:len(items)]
+        def flush(batch):
+            """First half of a batch: start the H2D copy of the page-locked batch the decode threads filled, enqueue every
+            kernel and the read-back copies; then finish the PREVIOUS batch while this one runs."""
+            H, W = batch.key
             tb = time.perf_counter()
-            k = model.forward_k(ring.to_device(slot, host), which_block=which_block)
+            items = [(None, file, index) for file, index in batch.items]
+            host = batch.host[:len(items)]
+            k = model.forward_k(host.to(dev, non_blocking=True), which_block=which_block)
             Hp, Wp = H // patch_size, W // patch_size
             rgb_lr, lr_size = None, None
             if image_color_lambda > 0:
@@ -587,13 +583,12 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
                 return h_
             h = {"items": items, "H": H, "W": W, "Hp": Hp, "Wp": Wp, "solve": solve, "evals": to_host(evals_d),
                  "evecs": to_host(evecs_d), "info": to_host(info_d), "masks": to_host(masks_d), "labels": to_host(labels_d),
-                 "k": to_host(k) if features_dir else None, "keep": (k, evals_d, evecs_d, info_d, masks_d, labels_d)}
+                 "k": to_host(k) if features_dir else None, "keep": (k, evals_d, evecs_d, info_d, masks_d, labels_d),
+                 "batch": batch}
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
             h["event"] = ev
-            tc = time.perf_counter()
-            tm["stage"] += tb - ta
-            tm["launch"] += tc - tb
+            tm["launch"] += time.perf_counter() - tb
             in_flight.append(h)
             while len(in_flight) > 1:
                 finish(in_flight.pop(0))
@@ -605,38 +600,24 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
                 print(f"Skipping existing file {str(Path(eigs_dir) / (file[:-4] + '.pth'))}")
             else:
                 todo.append(i)
-        # Images are grouped by shape. As soon as a decoded image arrives it is given a row of its group's page-locked
-        # batch and the copy into it runs on the staging pool (GIL-free) while this thread keeps pulling images; a group
-        # is flushed when it is full, or early (largest first) when too many images are waiting.
-        cap = max(1, int(batch_size))
-        groups: Dict[tuple, dict] = {}
-        pending = 0
-
-        def flush_group(key):
-            nonlocal pending
-            group = groups.pop(key)
-            pending -= len(group["items"])
-            flush(key, group)
-
-        for image, file, index in io_pipeline.ImagePrefetcher(dataset.__getitem__, todo, num_workers, lookahead=cap):
-            key = (int(image.shape[0]), int(image.shape[1]))
-            ring = rings.get(key)
-            if ring is None:
-                # page-locked memory per shape: 3 batches. Data sets with very many distinct sizes get small batches for
-                # the sizes that turn up late (bounded host memory; the common sizes come first in practice)
-                ring = rings[key] = io_pipeline.PinnedRing(key, cap if len(rings) < 12 else min(cap, 8), dev, slots=3)
-            group = groups.get(key)
-            if group is None:
-                group = groups[key] = {"slot": ring.begin(), "items": [], "futures": []}
-            group["futures"].append(ring.copy_async(group["slot"], len(group["items"]), image))
-            group["items"].append((None, file, index))   # (the pixels now live in the page-locked batch)
-            pending += 1
-            if len(group["items"]) >= ring.capacity:
-                flush_group(key)
-            elif pending > 8 * cap:
-                flush_group(max(groups, key=lambda k_: len(groups[k_]["items"])))
-        for key in list(groups.keys()):
-            flush_group(key)
+        # The decode threads group the images by shape and write them straight into page-locked batches
+        # (io_pipeline.BatchAssembler); this thread only sees completed batches.
+        if dataset.transform is None:
+            load = dataset.load_raw
+        else:
+            def load(i):
+                image, file, index = dataset[i]
+                return image.numpy(), False, file, index
+        assembler = io_pipeline.BatchAssembler(load, todo, max(1, int(batch_size)), num_workers)
+        it = iter(assembler)
+        while True:
+            ta = time.perf_counter()
+            batch = next(it, None)
+            tm["decode_wait"] += time.perf_counter() - ta
+            if batch is None:
+                break
+            flush(batch)
+        tm["pinned_alloc"] = assembler.alloc_seconds
         while in_flight:
             finish(in_flight.pop(0))
     seconds = time.perf_counter() - t_start
@@ -646,5 +627,6 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
     if all_failed:
         raise _lib.DssError(f"eigensolver did not converge for {len(all_failed)} image(s): {all_failed[:8]}")
     return {"images": len(todo), "seconds": seconds, "images_per_s": len(todo) / max(seconds, 1e-9),
-            "main_thread_seconds": {"pinned_staging": tm["stage"], "kernel_launches": tm["launch"],
+            "main_thread_seconds": {"waiting_for_decoders": tm["decode_wait"],
+                                    "pinned_alloc_in_decoders": tm["pinned_alloc"], "kernel_launches": tm["launch"],
                                     "waiting_for_gpu": tm["wait_gpu"], "writer_submit": tm["submit"], "total": seconds}}

@@ -30,6 +30,21 @@ def read_image_rgb(path) -> np.ndarray:
         return np.asarray(Image.open(str(path)).convert("RGB"))
 
 
+def read_image_raw(path):
+    """First half of read_image_rgb: (pixels, is_bgr). The colour swap is left to the caller so that it can write the
+    RGB image straight into a page-locked batch row (io_pipeline.PinnedRing.convert_async) instead of into a temporary
+    that is then copied."""
+    try:
+        import cv2
+        img = cv2.imread(str(path))
+        if img is None:
+            raise IOError(f"cannot decode {path}")
+        return img, True
+    except ImportError:
+        from PIL import Image
+        return np.asarray(Image.open(str(path)).convert("RGB")), False
+
+
 class ImagesDataset:
     """De-duplicated, sorted list of image files; items are (uint8 RGB HWC tensor, path, index).
 
@@ -51,6 +66,14 @@ class ImagesDataset:
         if self.transform is not None:
             image = self.transform(image)
         return image, path, index
+
+    def load_raw(self, index: int):
+        """(decoded pixels, is_bgr, path, index): __getitem__ without the BGR->RGB pass (see read_image_raw)."""
+        path = self.filenames[index]
+        full_path = Path(path) if self.root is None else self.root / path
+        assert full_path.is_file(), f"Not a file: {full_path}"
+        pixels, is_bgr = read_image_raw(full_path)
+        return pixels, is_bgr, path, index
 
     def __len__(self) -> int:
         return len(self.filenames)

@@ -6,6 +6,8 @@
                           bounded look-ahead, yielding items in order;
   * ``PinnedRing``       stages equally shaped uint8 images into a small ring of page-locked batches so that the
                           host->device copy is asynchronous and the decoder never waits for the GPU;
+  * ``BatchAssembler``   the two steps above in one: decode threads colour-swap each image straight into a row of a
+                          page-locked batch of its shape and hand over completed batches (used by extract_all);
   * ``AsyncWriter``      runs ``torch.save`` (same dict layouts, so ``torch.load`` consumers are unaffected) on writer
                           threads; ``close()`` waits for them and re-raises the first error;
   * ``ProcessWriter``    the same on writer PROCESSES, fed one message per GPU batch: torch.save is ~0.1-0.4 ms of pure
@@ -27,6 +29,10 @@ import torch
 
 
 def default_workers(cap: int = 32) -> int:
+    """Decode threads: DSS_IO_DECODE_THREADS, else min(cap, host threads - 1)."""
+    env = os.environ.get("DSS_IO_DECODE_THREADS")
+    if env:
+        return max(1, int(env))
     return max(1, min(cap, (os.cpu_count() or 2) - 1))
 
 
@@ -67,7 +73,7 @@ class PinnedRing:
     into the next slot (host memcpy), ``to_device`` starts the asynchronous H2D copy and returns the device batch; a
     slot is reused only after the copy that read it has completed (tracked with a CUDA event)."""
 
-    def __init__(self, shape: Tuple[int, int], capacity: int, device, slots: int = 2, copy_threads: int = 6):
+    def __init__(self, shape: Tuple[int, int], capacity: int, device, slots: int = 2, copy_threads: int = 8):
         H, W = shape
         self.device = device
         self.capacity = capacity
@@ -76,6 +82,7 @@ class PinnedRing:
         self.np_bufs = [b.numpy() for b in self.bufs]    # views of the page-locked memory
         self.events: List[Optional[torch.cuda.Event]] = [None] * slots
         self.next = 0
+        copy_threads = int(os.environ.get("DSS_IO_COPY_THREADS", copy_threads))
         self.copy_threads = copy_threads
         self._pool = ThreadPoolExecutor(copy_threads, thread_name_prefix="dss-stage") if copy_threads > 1 else None
 
@@ -118,12 +125,175 @@ class PinnedRing:
             return None
         return self._pool.submit(np.copyto, dst, src)
 
+    def convert_async(self, slot: int, j: int, pixels, is_bgr: bool):
+        """Like copy_async for a freshly decoded numpy image: a BGR image (cv2.imread) is colour-swapped DIRECTLY into
+        row j of the page-locked batch (one pass over the pixels instead of swap-into-a-temporary + copy)."""
+        import numpy as np
+        dst = self.np_bufs[slot][j]
+
+        def work():
+            if is_bgr:
+                import cv2
+                out = cv2.cvtColor(pixels, cv2.COLOR_BGR2RGB, dst=dst)
+                if out is not dst and not np.shares_memory(out, dst):   # cv2 reallocates when dst does not fit
+                    np.copyto(dst, out)
+            else:
+                np.copyto(dst, pixels)
+        if self._pool is None:
+            work()
+            return None
+        return self._pool.submit(work)
+
     def to_device(self, slot: int, host_batch: torch.Tensor) -> torch.Tensor:
         dev = host_batch.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self.events[slot] = ev
         return dev
+
+
+class HostBatch:
+    """One page-locked batch being filled by the decode workers (BatchAssembler)."""
+    __slots__ = ("key", "slot", "host", "np", "capacity", "items", "assigned", "filled", "closed")
+
+    def __init__(self, key, slot, host, capacity):
+        self.key, self.slot, self.host, self.np, self.capacity = key, slot, host, host.numpy(), capacity
+        self.items: List[tuple] = []          # (path, dataset index) per row
+        self.assigned = self.filled = 0
+        self.closed = False
+
+
+class BatchAssembler:
+    """Decode threads that write straight into page-locked batches, grouped by image shape.
+
+    Each worker takes the next dataset index, decodes the file (cv2 releases the interpreter lock), asks for a row of the
+    open batch of that image's shape and colour-swaps the pixels directly into that row: no per-image hand-over to the
+    consuming thread, no temporary RGB image, no staging copy. The consumer iterates over COMPLETED batches (in
+    completion order) and gives each one back with ``release`` once its host->device copy has finished; workers block
+    while all ``slots`` batches of a shape are in use, which bounds the page-locked memory.
+
+    ``load(i)`` -> (pixels uint8 [H, W, 3] numpy, is_bgr, path, index). A batch is completed when it is full, when more
+    than ``max_pending`` images sit in partly filled batches (the largest one is closed) or when the input is exhausted."""
+
+    def __init__(self, load: Callable, indices: Sequence[int], capacity: int, num_workers: Optional[int] = None,
+                 slots: int = 4, full_size_shapes: int = 12, small_capacity: int = 8, max_pending: Optional[int] = None):
+        self.load, self.indices = load, list(indices)
+        self.capacity, self.slots = max(1, int(capacity)), max(2, int(slots))
+        self.num_workers = num_workers if num_workers is not None else default_workers()
+        self.full_size_shapes, self.small_capacity = full_size_shapes, small_capacity
+        self.max_pending = max_pending if max_pending is not None else 8 * self.capacity
+        self._cv = threading.Condition()
+        self._it = iter(self.indices)
+        self._open = {}            # shape -> HostBatch being filled
+        self._rings = {}           # shape -> {"cap": rows, "free": [slot...], "bufs": [tensor...]}
+        self._pending = 0          # rows assigned in open batches
+        self._ready: "queue.Queue" = queue.Queue()
+        self._live = 0
+        self._stop = False
+        self.alloc_seconds = 0.0
+        self.threads: List[threading.Thread] = []
+
+    # -- called with self._cv held
+    def _close(self, b: HostBatch):
+        b.closed = True
+        self._open.pop(b.key, None)
+        self._pending -= b.assigned
+        if b.filled == b.assigned:
+            self._ready.put(b)
+
+    def _assign(self, key, path, index):
+        import time as _t
+        with self._cv:
+            while True:
+                if self._stop:
+                    raise RuntimeError("BatchAssembler stopped")
+                b = self._open.get(key)
+                if b is None:
+                    ring = self._rings.get(key)
+                    if ring is None:
+                        cap = self.capacity if len(self._rings) < self.full_size_shapes else min(self.capacity, self.small_capacity)
+                        ring = self._rings[key] = {"cap": cap, "free": [], "bufs": []}
+                    if not ring["free"] and len(ring["bufs"]) < self.slots:
+                        t0 = _t.perf_counter()   # page-locked allocation (torch's caching host allocator): lazily, per slot
+                        ring["bufs"].append(torch.empty(ring["cap"], key[0], key[1], 3, dtype=torch.uint8,
+                                                        pin_memory=torch.cuda.is_available()))
+                        ring["free"].append(len(ring["bufs"]) - 1)
+                        self.alloc_seconds += _t.perf_counter() - t0
+                    if not ring["free"]:
+                        self._cv.wait(0.5)
+                        continue
+                    slot = ring["free"].pop()
+                    b = self._open[key] = HostBatch(key, slot, ring["bufs"][slot], ring["cap"])
+                row = b.assigned
+                b.assigned += 1
+                b.items.append((path, index))
+                self._pending += 1
+                if b.assigned == b.capacity:
+                    self._close(b)
+                elif self._pending > self.max_pending:
+                    self._close(max(self._open.values(), key=lambda g: g.assigned))
+                return b, row
+
+    def _worker(self):
+        import numpy as np
+        try:
+            while True:
+                with self._cv:
+                    i = next(self._it, None) if not self._stop else None
+                if i is None:
+                    break
+                pixels, is_bgr, path, index = self.load(i)
+                b, row = self._assign((int(pixels.shape[0]), int(pixels.shape[1])), path, index)
+                dst = b.np[row]
+                if is_bgr:
+                    import cv2
+                    out = cv2.cvtColor(pixels, cv2.COLOR_BGR2RGB, dst=dst)
+                    if out is not dst and not np.shares_memory(out, dst):   # cv2 reallocates when dst does not fit
+                        np.copyto(dst, out)
+                else:
+                    np.copyto(dst, pixels)
+                with self._cv:
+                    b.filled += 1
+                    if b.closed and b.filled == b.assigned:
+                        self._ready.put(b)
+        except BaseException as e:  # noqa: BLE001  (re-raised by the consumer)
+            self._ready.put(e)
+        finally:
+            with self._cv:
+                self._live -= 1
+                if self._live == 0:     # input exhausted and every row written: hand over the partly filled batches
+                    for b in list(self._open.values()):
+                        self._close(b)
+
+    def __iter__(self) -> Iterator[HostBatch]:
+        total = len(self.indices)
+        if total == 0:
+            return
+        n = max(1, min(self.num_workers, total))
+        self._live = n
+        self.threads = [threading.Thread(target=self._worker, name=f"dss-decode-{t}", daemon=True) for t in range(n)]
+        for t in self.threads:
+            t.start()
+        got = 0
+        try:
+            while got < total:
+                b = self._ready.get()
+                if isinstance(b, BaseException):
+                    raise b
+                got += b.assigned
+                yield b
+        finally:
+            with self._cv:
+                self._stop = True
+                self._cv.notify_all()
+            for t in self.threads:
+                t.join(timeout=10)
+
+    def release(self, b: HostBatch) -> None:
+        """The consumer is done with the batch's page-locked memory (its host->device copy has completed)."""
+        with self._cv:
+            self._rings[b.key]["free"].append(b.slot)
+            self._cv.notify_all()
 
 
 class AsyncWriter:
@@ -257,12 +427,17 @@ class ProcessWriter:
     def submit_batch(self, arrays, items) -> None:
         self._check()
         n = len(self.procs)
-        # split the batch's items over the writers (each message carries the arrays once; they are a few MB)
+        # split the batch over the writers in contiguous row ranges; each message carries only its rows of the arrays
+        rows = sorted(it_[1] for it_ in items)
+        per = -(-len(rows) // n)
         for w in range(n):
-            part = items[w::n]
-            if part:
-                self.q.put((arrays, part))
-                self.submitted += len(part)
+            sel = rows[w * per:(w + 1) * per]
+            if not sel:
+                continue
+            lo, hi = sel[0], sel[-1] + 1
+            part = [(path, j - lo, extra, fields) for path, j, extra, fields in items if lo <= j < hi]
+            self.q.put(({name: a[lo:hi] for name, a in arrays.items()}, part))
+            self.submitted += len(part)
 
     def flush(self, timeout: float = 600.0) -> int:
         import queue as _q

@@ -176,3 +176,69 @@ def test_gemm_gelu_erf_constants():
     assert err.max() < 8e-6, err.max()
     neg = (x < -1) & (x > -3)                               # relative accuracy down to -3 (values >= 4e-3; beyond that the
     assert np.all(err[neg] <= 2e-3 * np.abs(ref[neg]))      # 6e-6 absolute bound is below the fp16 normal range)
+
+
+def test_batch_assembler_groups_by_shape_and_delivers_every_image_once(tmp_path):
+    """io_pipeline.BatchAssembler (the decode side of extract_all): three image shapes, decode threads writing straight
+    into the batches, only two batches per shape so that workers must wait for release(); every file has to come out
+    exactly once, in a batch of its own shape, with the pixels cv2.imread + BGR->RGB gives (extract_utils.py:30-31)."""
+    import cv2
+    iop = load_pkg("io_pipeline"); utils = load_pkg("extract_utils")
+    rng = np.random.default_rng(0)
+    shapes = [(32, 48), (48, 32), (40, 40)]
+    names = []
+    for i in range(157):
+        H, W = shapes[i % 3 if i < 150 else 2]
+        name = f"im{i:04d}.png"
+        cv2.imwrite(str(tmp_path / name), rng.integers(0, 256, (H, W, 3), dtype=np.uint8))
+        names.append(name)
+    ds = utils.ImagesDataset(names, str(tmp_path))
+    asm = iop.BatchAssembler(ds.load_raw, range(len(ds)), capacity=16, num_workers=5, slots=2)
+    seen = {}
+    held = []
+    for b in asm:
+        assert 1 <= b.assigned <= 16 and b.filled == b.assigned and len(b.items) == b.assigned
+        for row, (path, index) in enumerate(b.items):
+            assert index not in seen
+            seen[index] = (b.key, b.host[row].clone())
+        held.append(b)
+        if len(held) > 1:            # like extract_all: a batch is given back one batch later
+            asm.release(held.pop(0))
+    assert sorted(seen) == list(range(len(ds)))
+    for index, (key, pixels) in seen.items():
+        want, path, idx = ds[index]
+        assert idx == index and key == tuple(want.shape[:2])
+        assert torch.equal(pixels, want)
+    # an unreadable file surfaces as an exception in the consumer, not as a hang
+    (tmp_path / "broken.png").write_bytes(b"not an image")
+    bad = utils.ImagesDataset(names[:8] + ["broken.png"], str(tmp_path))
+    with pytest.raises(IOError):
+        for b in iop.BatchAssembler(bad.load_raw, range(len(bad)), capacity=4, num_workers=3):
+            pass
+
+
+def test_process_writer_splits_a_batch_into_row_ranges(tmp_path):
+    """ProcessWriter.submit_batch sends each writer only its rows; the files must hold the row of their own image."""
+    iop = load_pkg("io_pipeline")
+    arrays = {"v": np.arange(10 * 3, dtype=np.float32).reshape(10, 3)}
+    items = [(str(tmp_path / f"f{j}.pth"), j, {"id": f"f{j}"}, {"row": ("slice", "v"), "n": ("tensor0d", j)})
+             for j in range(10) if j != 4]
+    sent = []
+
+    class Fake(iop.ProcessWriter):
+        def __init__(self):
+            self.procs = [None] * 3; self.submitted = 0; self.done = 0
+            self.q = type("Q", (), {"put": lambda self_, m: sent.append(m)})()
+
+        def _check(self):
+            pass
+    Fake().submit_batch(arrays, items)
+    got = {}
+    for arrs, part in sent:
+        for path, j, extra, fields in part:
+            got[extra["id"]] = iop._materialise(arrs, j, extra, fields)
+    assert sorted(got) == sorted(f"f{j}" for j in range(10) if j != 4)
+    for name, d in got.items():
+        j = int(name[1:])
+        assert torch.equal(d["row"], torch.from_numpy(arrays["v"][j])) and int(d["n"]) == j
+    assert sum(a["v"].shape[0] for a, _ in sent) <= 10

@@ -353,8 +353,8 @@ def test_extract_all_host_pipeline_throughput(cuda, tmp_path):
         names.append(name)
     (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
     # warm-up (module load, weights, workspace allocation) on a small list
-    (tmp_path / "warm.txt").write_text("\n".join(names[:64]) + "\n")
-    ex.extract_all(str(tmp_path / "warm.txt"), str(root), "dino_vits16", None, str(tmp_path / "warm"), K=5, batch_size=64, seed=0)
+    (tmp_path / "warm.txt").write_text("\n".join(names[:256]) + "\n")
+    ex.extract_all(str(tmp_path / "warm.txt"), str(root), "dino_vits16", None, str(tmp_path / "warm"), K=5, batch_size=128, seed=0)
     t0 = time.perf_counter()
     st = ex.extract_all(str(tmp_path / "list.txt"), str(root), "dino_vits16", None, str(tmp_path / "eigs"), K=5, batch_size=128,
                         seed=0)
