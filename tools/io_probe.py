@@ -7,56 +7,64 @@ sys.path.insert(0, str(ROOT / "tests"))
 from conftest import load_pkg  # noqa: E402
 import numpy as np, cv2, torch  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-ex = load_pkg("extract"); iop = load_pkg("io_pipeline"); synth = load_pkg("synth")
-tmp = Path(tempfile.mkdtemp())
-root = tmp / "images"; root.mkdir()
-imgs = synth.blobs_batch(64, 480, 480, seed0=0).numpy()
-names = []
-for i in range(n):
-    name = f"im{i:05d}.jpg"
-    if i < 64:
-        cv2.imwrite(str(root / name), cv2.cvtColor(imgs[i], cv2.COLOR_RGB2BGR), [cv2.IMWRITE_JPEG_QUALITY, 90])
-    else:
-        shutil.copyfile(root / names[i % 64], root / name)
-    names.append(name)
-(tmp / "list.txt").write_text("\n".join(names) + "\n")
-(tmp / "warm.txt").write_text("\n".join(names[:128]) + "\n")
-ex.extract_all(str(tmp / "warm.txt"), str(root), "dino_vits16", None, str(tmp / "warm"), K=5, batch_size=128, seed=0)
 run = 0
-def go(label, batch=128, writer="process", wout=4, **env):
-    global run
-    run += 1
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update({k: str(v) for k, v in env.items()})
-    si = float(env.get("SWITCH", 0.005)); sys.setswitchinterval(si)
-    st = ex.extract_all(str(tmp / "list.txt"), str(root), "dino_vits16", None, str(tmp / f"eigs{run}"), K=5, batch_size=batch, seed=0, writer=writer, num_workers_out=wout)
-    sys.setswitchinterval(0.005)
-    for k, v in old.items():
-        if v is None: os.environ.pop(k, None)
-        else: os.environ[k] = v
-    print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, flush=True)
-    shutil.rmtree(tmp / f"eigs{run}", ignore_errors=True)
 
-for rep in range(2):
-    go("default")
-    go("decode16", DSS_IO_DECODE_THREADS=16)
-    go("decode48", DSS_IO_DECODE_THREADS=48)
-    go("decode64", DSS_IO_DECODE_THREADS=64)
-    go("decode24", DSS_IO_DECODE_THREADS=24)
-    go("decode96", DSS_IO_DECODE_THREADS=96)
-    go("writers8", wout=8)
-    go("writers2", wout=2)
-    go("switch0.5ms", SWITCH=0.0005)
-    go("switch0.1ms", SWITCH=0.0001)
-    go("batch256", batch=256)
-    go("batch64", batch=64)
-    go("threadwriter", writer="thread")
-# decode only
-ds = ex.utils.ImagesDataset(names, str(root))
-for w in (16, 32, 64):
-    t0 = time.perf_counter(); c = sum(1 for _ in iop.ImagePrefetcher(ds.load_raw, range(len(ds)), num_workers=w)); dt = time.perf_counter() - t0
-    print("PROBE decode_only_raw", w, round(c / dt))
-    t0 = time.perf_counter(); c = sum(1 for _ in iop.ImagePrefetcher(ds.__getitem__, range(len(ds)), num_workers=w)); dt = time.perf_counter() - t0
-    print("PROBE decode_only_rgb", w, round(c / dt))
-shutil.rmtree(tmp, ignore_errors=True)
+
+def main():
+    global run
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+    ex = load_pkg("extract"); iop = load_pkg("io_pipeline"); synth = load_pkg("synth")
+    tmp = Path(tempfile.mkdtemp())
+    root = tmp / "images"; root.mkdir()
+    imgs = synth.blobs_batch(64, 480, 480, seed0=0).numpy()
+    names = []
+    for i in range(n):
+        name = f"im{i:05d}.jpg"
+        if i < 64:
+            cv2.imwrite(str(root / name), cv2.cvtColor(imgs[i], cv2.COLOR_RGB2BGR), [cv2.IMWRITE_JPEG_QUALITY, 90])
+        else:
+            shutil.copyfile(root / names[i % 64], root / name)
+        names.append(name)
+    (tmp / "list.txt").write_text("\n".join(names) + "\n")
+    (tmp / "warm.txt").write_text("\n".join(names[:128]) + "\n")
+    ex.extract_all(str(tmp / "warm.txt"), str(root), "dino_vits16", None, str(tmp / "warm"), K=5, batch_size=128, seed=0)
+    def go(label, batch=128, writer="process", wout=4, **env):
+        global run
+        run += 1
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update({k: str(v) for k, v in env.items()})
+        si = float(env.get("SWITCH", 0.005)); sys.setswitchinterval(si)
+        st = ex.extract_all(str(tmp / "list.txt"), str(root), "dino_vits16", None, str(tmp / f"eigs{run}"), K=5, batch_size=batch, seed=0, writer=writer, num_workers_out=wout)
+        sys.setswitchinterval(0.005)
+        for k, v in old.items():
+            if v is None: os.environ.pop(k, None)
+            else: os.environ[k] = v
+        print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, flush=True)
+        shutil.rmtree(tmp / f"eigs{run}", ignore_errors=True)
+
+    for rep in range(2):
+        go("default")
+        go("decode16", DSS_IO_DECODE_THREADS=16)
+        go("decode48", DSS_IO_DECODE_THREADS=48)
+        go("decode64", DSS_IO_DECODE_THREADS=64)
+        go("decode24", DSS_IO_DECODE_THREADS=24)
+        go("decode96", DSS_IO_DECODE_THREADS=96)
+        go("writers8", wout=8)
+        go("writers2", wout=2)
+        go("switch0.5ms", SWITCH=0.0005)
+        go("switch0.1ms", SWITCH=0.0001)
+        go("batch256", batch=256)
+        go("batch64", batch=64)
+        go("threadwriter", writer="thread")
+    # decode only
+    ds = ex.utils.ImagesDataset(names, str(root))
+    for w in (16, 32, 64):
+        t0 = time.perf_counter(); c = sum(1 for _ in iop.ImagePrefetcher(ds.load_raw, range(len(ds)), num_workers=w)); dt = time.perf_counter() - t0
+        print("PROBE decode_only_raw", w, round(c / dt))
+        t0 = time.perf_counter(); c = sum(1 for _ in iop.ImagePrefetcher(ds.__getitem__, range(len(ds)), num_workers=w)); dt = time.perf_counter() - t0
+        print("PROBE decode_only_rgb", w, round(c / dt))
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":   # the writer pool uses the 'spawn' start method: children re-import this module
+    main()
