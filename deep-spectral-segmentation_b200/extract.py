@@ -168,14 +168,20 @@ def _color_inputs(images_root, image_ids, W_lr, H_lr, which_color_matrix, dev):
     return torch.from_numpy((lr / 255.0).astype(np.float32)).to(dev)
 
 
+def _bad_rows(evals: torch.Tensor, evecs: torch.Tensor, info: torch.Tensor) -> List[int]:
+    """Rows of a batch (CPU tensors) whose solve did not reach the tolerance or came back non-finite. Three tensor
+    operations per batch: a per-image Python loop here cost more main-thread time than launching the kernels did."""
+    ok = (info[:, 1] != 0) & torch.isfinite(evecs).flatten(1).all(1) & torch.isfinite(evals).flatten(1).all(1)
+    return (~ok).nonzero().flatten().tolist()
+
+
 def _solve_with_retry(solve, n_images: int, N: int):
     """Runs ``solve(sel, max_steps)`` (sel = None for the whole batch, else a list of batch rows) and retries the images
     whose Lanczos run did not reach its tolerance or came back non-finite with the largest possible Krylov space
     (max_steps = N - 1). The reference's own safety net is a second eigsh call (which='SM', extract.py:226-234).
     Returns (eigenvalues, eigenvectors, info, failed rows) on the CPU."""
     evals, evecs, info = (t.cpu() for t in solve(None, 0))
-    bad = [i for i in range(n_images)
-           if int(info[i, 1]) == 0 or not bool(torch.isfinite(evecs[i]).all() and torch.isfinite(evals[i]).all())]
+    bad = _bad_rows(evals, evecs, info)
     failed = []
     if bad:
         ev2, vec2, info2 = (t.cpu() for t in solve(bad, max(N - 1, 1)))
@@ -516,8 +522,7 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
             items, H, W, Hp, Wp = h["items"], h["H"], h["W"], h["Hp"], h["Wp"]
             evals, evecs, info = h["evals"], h["evecs"], h["info"]
             n_img = len(items)
-            bad = [i for i in range(n_img) if int(info[i, 1]) == 0
-                   or not bool(torch.isfinite(evecs[i]).all() and torch.isfinite(evals[i]).all())]
+            bad = _bad_rows(evals, evecs, info)
             failed = []
             if bad:   # rare: largest possible Krylov space for the images that did not reach the tolerance
                 ev2, vec2, info2 = (t.cpu() for t in h["solve"](bad, max(Hp * Wp - 1, 1)))

@@ -385,8 +385,12 @@ def _writer_process_main(q, errq, doneq):
             if msg is None:
                 return
             arrays, items = msg
+            made = set()
             for path, j, extra, fields in items:
-                Path(path).parent.mkdir(parents=True, exist_ok=True)
+                parent = os.path.dirname(path)
+                if parent not in made:      # one mkdir per directory and message, not per file
+                    os.makedirs(parent, exist_ok=True)
+                    made.add(parent)
                 tmp = f"{path}.tmp{os.getpid()}"
                 torch.save(_materialise(arrays, j, extra, fields), tmp)
                 os.replace(tmp, path)

@@ -42,7 +42,44 @@ def main():
         print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, flush=True)
         shutil.rmtree(tmp / f"eigs{run}", ignore_errors=True)
 
-    for rep in range(2):
+    # what one .pth costs on this box's file systems (torch.save + rename, like the writers): serial and 4 processes
+    import subprocess
+    code = ("import torch, os, sys, time\n"
+            "d = sys.argv[1]; n = int(sys.argv[2]); tag = sys.argv[3]\n"
+            "obj = {'eigenvalues': torch.randn(5), 'eigenvectors': torch.randn(5, 900)}\n"
+            "t = time.perf_counter()\n"
+            "for i in range(n):\n"
+            "    torch.save(obj, f'{d}/{tag}{i}.tmp'); os.replace(f'{d}/{tag}{i}.tmp', f'{d}/{tag}{i}.pth')\n"
+            "print((time.perf_counter() - t) / n * 1e6)\n")
+    for label, base in (("tmpdir", tempfile.gettempdir()), ("devshm", "/dev/shm")):
+        if not os.path.isdir(base):
+            continue
+        d = tempfile.mkdtemp(dir=base)
+        one = subprocess.run([sys.executable, "-c", code, d, "500", "a"], capture_output=True, text=True).stdout.strip()
+        ps = [subprocess.Popen([sys.executable, "-c", code, d, "500", f"p{k}_"], stdout=subprocess.PIPE, text=True) for k in range(4)]
+        four = [p_.communicate()[0].strip() for p_ in ps]
+        print("PROBE fs", label, base, "us_per_file serial", one, "4procs_same_dir", four, flush=True)
+        shutil.rmtree(d, ignore_errors=True)
+    shm = Path(tempfile.mkdtemp(dir="/dev/shm")) if os.path.isdir("/dev/shm") else None
+
+    def go_shm(label, **kw):
+        nonlocal tmp
+        if shm is None:
+            return
+        keep = tmp
+        # only the outputs move to tmpfs; the JPEGs stay where they are
+        global run
+        run += 1
+        st = ex.extract_all(str(keep / "list.txt"), str(root), "dino_vits16", None, str(shm / f"eigs{run}"), K=5, batch_size=128, seed=0, **kw)
+        print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, flush=True)
+        shutil.rmtree(shm / f"eigs{run}", ignore_errors=True)
+
+    for rep in range(3):
+        go("default")
+        go_shm("out_on_devshm")
+    if shm is not None:
+        shutil.rmtree(shm, ignore_errors=True)
+    for rep in range(0):
         go("default")
         go("decode16", DSS_IO_DECODE_THREADS=16)
         go("decode48", DSS_IO_DECODE_THREADS=48)
