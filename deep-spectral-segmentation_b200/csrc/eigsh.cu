@@ -24,6 +24,7 @@ namespace dss {
 
 constexpr int EIG_THREADS = 512;
 constexpr int EIG_WARPS = EIG_THREADS / 32;
+constexpr bool EIG_PAIR_DEFAULT = false;   // (A/B pending) two 256-thread CTAs per SM when shared memory allows
 constexpr int EIG_MAX_K = 64;
 
 constexpr int EIG_STRIP_CH = 4;                    // float4 column chunks per lane and strip
@@ -48,6 +49,7 @@ struct EigParams {
   float tol;
 };
 
+template <int NW>
 __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
   v = warp_sum(v);
   __syncthreads();  // protect red from the previous use
@@ -55,7 +57,7 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
   __syncthreads();
   double s = 0.0;
 #pragma unroll
-  for (int i = 0; i < EIG_WARPS; ++i) s += red[i];
+  for (int i = 0; i < NW; ++i) s += red[i];
   return s;
 }
 
@@ -102,10 +104,11 @@ __host__ __device__ inline size_t eig_double_bytes(int mmax) {
 
 // R = rows per warp and pass of the mat-vec (R independent 128-bit loads in flight per lane), MINB = CTAs per SM the
 // register budget is sized for: <2, 2> for N <= 1024 (two images per SM), <4, 1> beyond.
-template <int R, int MINB>
-__global__ void __launch_bounds__(EIG_THREADS, MINB)
+template <int R, int MINB, int NT>
+__global__ void __launch_bounds__(NT, MINB)
 lanczos_laplacian_kernel(EigParams p) {
-  constexpr int PRE = MINB == 2 ? 2 : EIG_STRIP_CH;   // column blocks whose loads are in flight together
+  constexpr int NW = NT / 32;                          // warps of this instantiation (the layout keeps room for NW)
+  constexpr int PRE = (MINB == 2 && NT == NT) ? 2 : EIG_STRIP_CH;   // column blocks whose loads are in flight together
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int N = p.N, Npad = p.Npad, mmax = p.mmax, K = p.K, ldw = p.ldw;
   const bool lapn = p.mode == 0, plain = p.mode == 2;
@@ -126,7 +129,7 @@ lanczos_laplacian_kernel(EigParams p) {
   float* u0 = dsc + Npad;                                    // [Npad] deflated null vector (unit 2-norm)
   float* ycol = u0 + Npad;                                   // [Npad] column part of the symmetric mat-vec
   const int stripw = Npad < EIG_STRIP ? Npad : EIG_STRIP;
-  float* colbuf = ycol + Npad;                               // [EIG_WARPS][stripw] per-warp column accumulators
+  float* colbuf = ycol + Npad;                               // [NW][stripw] per-warp column accumulators
   float* coef = colbuf + (size_t)EIG_WARPS * stripw;         // [mmax + 2]
   __shared__ int s_flag;
 
@@ -140,11 +143,11 @@ lanczos_laplacian_kernel(EigParams p) {
     __syncthreads();
     // ---- degree D = W 1  (row_sum, extract_utils.py:217), clamp < 1e-12 -> 1 (:218)
     if (plain) {              // plain top-K mode: no degree
-      for (int i = tid; i < N; i += EIG_THREADS) wv[i] = 1.0f;
+      for (int i = tid; i < N; i += NT) wv[i] = 1.0f;
     } else if (p.deg != nullptr) {   // accumulated by the affinity epilogue: no pass over W
-      for (int i = tid; i < N; i += EIG_THREADS) wv[i] = __ldg(p.deg + (size_t)img * N + i);
+      for (int i = tid; i < N; i += NT) wv[i] = __ldg(p.deg + (size_t)img * N + i);
     } else {
-      for (int r = warp; r < N; r += EIG_WARPS) {
+      for (int r = warp; r < N; r += NW) {
         const float4* row = reinterpret_cast<const float4*>(W + (size_t)r * ldw);
         float s0 = 0.f, s1 = 0.f;
         for (int i = lane; i < (Npad >> 2); i += 32) {  // pad columns [N, Npad) are zero
@@ -157,7 +160,7 @@ lanczos_laplacian_kernel(EigParams p) {
     }
     __syncthreads();
     double part = 0.0;
-    for (int i = tid; i < Npad; i += EIG_THREADS) {
+    for (int i = tid; i < Npad; i += NT) {
       float dg = 0.f;
       if (i < N) {
         dg = wv[i];
@@ -166,8 +169,8 @@ lanczos_laplacian_kernel(EigParams p) {
       }
       wv[i] = dg;
     }
-    const double sumD = block_sum(part, red, tid);
-    for (int i = tid; i < Npad; i += EIG_THREADS) {
+    const double sumD = block_sum<NW>(part, red, tid);
+    for (int i = tid; i < Npad; i += NT) {
       const float dg = wv[i];
       if (i < N) {
         if (lapn) {
@@ -192,20 +195,20 @@ lanczos_laplacian_kernel(EigParams p) {
     bool have_theta = false;
     if (Kw > 0) {
       // ---- start vector: deterministic pseudo-random, orthogonal to u0
-      for (int i = tid; i < Npad; i += EIG_THREADS) wv[i] = (i < N) ? hash_uniform((uint32_t)i, 0x1234567u) : 0.f;
+      for (int i = tid; i < Npad; i += NT) wv[i] = (i < N) ? hash_uniform((uint32_t)i, 0x1234567u) : 0.f;
       __syncthreads();
       for (int pass = 0; pass < 2; ++pass) {
         double d = 0.0;
-        for (int i = tid; i < N; i += EIG_THREADS) d += (double)wv[i] * (double)u0[i];
-        const float c = (float)block_sum(d, red, tid);
-        for (int i = tid; i < N; i += EIG_THREADS) wv[i] = fmaf(-c, u0[i], wv[i]);
+        for (int i = tid; i < N; i += NT) d += (double)wv[i] * (double)u0[i];
+        const float c = (float)block_sum<NW>(d, red, tid);
+        for (int i = tid; i < N; i += NT) wv[i] = fmaf(-c, u0[i], wv[i]);
         __syncthreads();
       }
       {
         double d = 0.0;
-        for (int i = tid; i < N; i += EIG_THREADS) d += (double)wv[i] * (double)wv[i];
-        const float inv = (float)(1.0 / sqrt(block_sum(d, red, tid)));
-        for (int i = tid; i < Npad; i += EIG_THREADS) {
+        for (int i = tid; i < N; i += NT) d += (double)wv[i] * (double)wv[i];
+        const float inv = (float)(1.0 / sqrt(block_sum<NW>(d, red, tid)));
+        for (int i = tid; i < Npad; i += NT) {
           const float v = (i < N) ? wv[i] * inv : 0.f;
           vcur[i] = v;
           basis[i] = v;
@@ -216,7 +219,7 @@ lanczos_laplacian_kernel(EigParams p) {
       double anorm = 1.0;
       for (int j = 0; j < mmax; ++j) {
         // ---- mat-vec  w = S v  (lapnorm)   or   w = (W - D) v  (unnormalised: top of -(D-W)), upper triangle of W only
-        for (int i = tid; i < Npad; i += EIG_THREADS) {
+        for (int i = tid; i < Npad; i += NT) {
           xs[i] = lapn ? dsc[i] * vcur[i] : vcur[i];
           wv[i] = 0.f;   // row part, accumulated strip by strip by the warp that owns the row
         }
@@ -229,7 +232,7 @@ lanczos_laplacian_kernel(EigParams p) {
           const float4* x4 = reinterpret_cast<const float4*>(xs);
           const float4* W4 = reinterpret_cast<const float4*>(W);
           // R consecutive rows per warp and pass (r % R == 0, so their diagonal elements share one 4-column chunk)
-          for (int r = warp * R; r < N && r < s1; r += EIG_WARPS * R) {
+          for (int r = warp * R; r < N && r < s1; r += NW * R) {
             // 32-bit chunk offsets from the image's base (N * ldw < 2^31): one IMAD.WIDE per load instead of a 64-bit
             // row pointer that the 64-register budget forces the compiler to rebuild in every block
             const float4* rowp[R];
@@ -320,15 +323,15 @@ lanczos_laplacian_kernel(EigParams p) {
             if (4 * cl < s1 - s0) cb[cl] = colacc[k];
           }
           __syncthreads();
-          for (int c = tid; c < s1 - s0; c += EIG_THREADS) {
+          for (int c = tid; c < s1 - s0; c += NT) {
             float sc = 0.f;
 #pragma unroll
-            for (int w2 = 0; w2 < EIG_WARPS; ++w2) sc += colbuf[(size_t)w2 * stripw + c];
+            for (int w2 = 0; w2 < NW; ++w2) sc += colbuf[(size_t)w2 * stripw + c];
             ycol[s0 + c] = sc;
           }
           __syncthreads();
         }
-        for (int i = tid; i < Npad; i += EIG_THREADS) {
+        for (int i = tid; i < Npad; i += NT) {
           const float sa = wv[i] + ycol[i];
           wv[i] = (i < N) ? (lapn ? dsc[i] * sa : (plain ? sa : sa - dsc[i] * xs[i])) : 0.f;
         }
@@ -336,14 +339,14 @@ lanczos_laplacian_kernel(EigParams p) {
         // ---- full re-orthogonalisation (CGS2) against u0, v_0..v_j ; alpha_j = sum of the v_j coefficients
         double aj = 0.0;
         for (int pass = 0; pass < 2; ++pass) {
-          for (int i = warp; i < j + 2; i += EIG_WARPS) {
+          for (int i = warp; i < j + 2; i += NW) {
             const float* a = (i == 0) ? u0 : ((i - 1 == j) ? vcur : basis + (size_t)(i - 1) * Npad);
             const float c = warp_dot(a, wv, N, lane);
             if (lane == 0) coef[i] = c;
           }
           __syncthreads();
           aj += (double)coef[j + 1];
-          for (int i = tid; i < N; i += EIG_THREADS) {
+          for (int i = tid; i < N; i += NT) {
             float acc = coef[0] * u0[i];
             for (int t = 0; t < j; ++t) acc = fmaf(coef[t + 1], basis[(size_t)t * Npad + i], acc);
             acc = fmaf(coef[j + 1], vcur[i], acc);
@@ -352,8 +355,8 @@ lanczos_laplacian_kernel(EigParams p) {
           __syncthreads();
         }
         double d = 0.0;
-        for (int i = tid; i < N; i += EIG_THREADS) d += (double)wv[i] * (double)wv[i];
-        const double bj = sqrt(block_sum(d, red, tid));
+        for (int i = tid; i < N; i += NT) d += (double)wv[i] * (double)wv[i];
+        const double bj = sqrt(block_sum<NW>(d, red, tid));
         if (tid == 0) {
           alpha[j] = aj;
           beta[j] = bj;
@@ -365,7 +368,7 @@ lanczos_laplacian_kernel(EigParams p) {
         if (!breakdown) {
           const float inv = (float)(1.0 / bj);
           float* vn = basis + (size_t)(j + 1) * Npad;
-          for (int i = tid; i < Npad; i += EIG_THREADS) {
+          for (int i = tid; i < Npad; i += NT) {
             const float v = (i < N) ? wv[i] * inv : 0.f;
             vcur[i] = v;
             vn[i] = v;
@@ -398,7 +401,7 @@ lanczos_laplacian_kernel(EigParams p) {
           }
           const double span = fmax(gh - gl, 1e-30);
           gl -= 1e-3 * span; gh += 1e-3 * span;
-          for (int k = warp; k < kg; k += EIG_WARPS) {
+          for (int k = warp; k < kg; k += NW) {
             // k-th largest eigenvalue = ascending index t = n-1-k ; lambda_t >= x  <=>  count(x) <= t
             const int t = n - 1 - k;
             double lo = gl, hi = gh;
@@ -498,7 +501,7 @@ lanczos_laplacian_kernel(EigParams p) {
     {
       const float c0 = lapn ? (float)(1.0 / sqrt(sumD)) : (float)(1.0 / sqrt((double)N));
       if (!plain)
-        for (int i = tid; i < N; i += EIG_THREADS) evec[i] = c0;
+        for (int i = tid; i < N; i += NT) evec[i] = c0;
       if (tid == 0) {
         if (!plain) {
           ev[0] = 0.f;
@@ -514,29 +517,29 @@ lanczos_laplacian_kernel(EigParams p) {
     for (int k = 0; k < Kw; ++k) {
       float* out = evec + (size_t)(k + off) * N;
       if (k >= have) {  // degenerate request (K-1 > steps possible): fill with NaN
-        for (int i = tid; i < N; i += EIG_THREADS) out[i] = __int_as_float(0x7fc00000);
+        for (int i = tid; i < N; i += NT) out[i] = __int_as_float(0x7fc00000);
         if (tid == 0) ev[k + off] = __int_as_float(0x7fc00000);
         continue;
       }
       const double* zs = triS + (size_t)k * mmax;
       double d = 0.0;
-      for (int i = tid; i < N; i += EIG_THREADS) {
+      for (int i = tid; i < N; i += NT) {
         float acc = 0.f;
         for (int t = 0; t < n; ++t) acc = fmaf((float)zs[t], basis[(size_t)t * Npad + i], acc);
         wv[i] = acc;
         d += (double)acc * (double)acc;
       }
-      const float inv = (float)(1.0 / sqrt(block_sum(d, red, tid)));
+      const float inv = (float)(1.0 / sqrt(block_sum<NW>(d, red, tid)));
       int pos = 0;
-      for (int i = tid; i < N; i += EIG_THREADS) {
+      for (int i = tid; i < N; i += NT) {
         const float v = lapn ? wv[i] * inv * dsc[i] : wv[i] * inv;
         wv[i] = v;
         pos += v > 0.f;
       }
-      const int npos = (int)(block_sum((double)pos, red, tid) + 0.5);
+      const int npos = (int)(block_sum<NW>((double)pos, red, tid) + 0.5);
       // sign rule (extract.py:237-240): flip iff 0.5 < mean(v > 0) < 1.0
       const float sgn = (2 * npos > N && npos < N) ? -1.f : 1.f;
-      for (int i = tid; i < N; i += EIG_THREADS) out[i] = sgn * wv[i];
+      for (int i = tid; i < N; i += NT) out[i] = sgn * wv[i];
       if (tid == 0) {
         ev[k + off] = lapn ? (float)(1.0 - theta[k]) : (plain ? (float)theta[k] : (float)(-theta[k]));
         if (p.resid) p.resid[(size_t)img * K + k + off] = (float)resid_s[k];
@@ -560,15 +563,27 @@ static int eig_resolve(int N, int K, int max_steps) {
   return mmax;
 }
 
+// CTAs per SM: 2 when two images' shared memory fits (N <= ~2000) -- the <4, 2, 256> instantiation, two 256-thread CTAs
+// at 128 registers, so that one image's vector phases (reorthogonalisation, Ritz test) overlap the other's mat-vec --
+// else 1 (<4, 1, 512>). DSS_EIG_VARIANT (tuning): 1 forces <2, 2, 512>, 2 forces <4, 1, 512>, 3 forces the pairing.
+static int eig_variant() {
+  static const int variant = [] { const char* e = getenv("DSS_EIG_VARIANT"); return e ? atoi(e) : 0; }();
+  return variant;
+}
+
+static int eig_per_sm(int Npad, int mmax) {
+  const size_t smem = eig_smem_bytes(Npad, mmax);
+  const int fit = (int)((size_t)(220 * 1024) / (smem + 1024));
+  const int v = eig_variant();
+  if (v == 2) return 1;
+  if (v == 1 || v == 3) return fit >= 2 ? 2 : 1;
+  return (EIG_PAIR_DEFAULT && fit >= 2) ? 2 : 1;
+}
+
 static int eig_grid(int B, int Npad, int mmax) {
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  const size_t smem = eig_smem_bytes(Npad, mmax);
-  int per_sm = (int)((size_t)(220 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);  // 512 threads, <=64 regs => at most 2 CTAs / SM
-  static const int variant = [] { const char* e = getenv("DSS_EIG_VARIANT"); return e ? atoi(e) : 0; }();
-  if ((Npad > EIG_SMALL_N && variant != 1) || variant == 2) per_sm = 1;   // the <4, 1> instantiation: one CTA per SM
-  int g = sms * per_sm;
+  const int g = sms * eig_per_sm(Npad, mmax);
   return B < g ? B : g;
 }
 
@@ -615,13 +630,16 @@ static int eigsh_launch(const float* Wmat, const float* deg, int ldw, int B, int
     return DSS_ERR_UNSUPPORTED;
   }
   LaunchScope scope(static_cast<cudaStream_t>(stream), KC_EIGSH);
-  static const int variant = [] { const char* e = getenv("DSS_EIG_VARIANT"); return e ? atoi(e) : 0; }();   // tuning
-  if ((p.Npad <= EIG_SMALL_N && variant != 2) || variant == 1) {
-    DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lanczos_laplacian_kernel<2, 2><<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  const int per_sm = eig_per_sm(p.Npad, p.mmax);
+  if (per_sm == 2 && eig_variant() == 1) {
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<2, 2, EIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lanczos_laplacian_kernel<2, 2, EIG_THREADS><<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  } else if (per_sm == 2) {
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<4, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lanczos_laplacian_kernel<4, 2, 256><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
   } else {
-    DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lanczos_laplacian_kernel<4, 1><<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(lanczos_laplacian_kernel<4, 1, EIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lanczos_laplacian_kernel<4, 1, EIG_THREADS><<<grid, EIG_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   }
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
