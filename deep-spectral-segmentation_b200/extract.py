@@ -507,6 +507,7 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
     filenames = Path(images_list).read_text().splitlines()
     dataset = utils.ImagesDataset(filenames=filenames, images_root=images_root)
     all_failed: List[str] = []
+    decode_threads: dict = {}
     import time
     t_start = time.perf_counter()   # model set-up (weights, packing) is done: what follows is the per-image pipeline
 
@@ -623,6 +624,8 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
                 break
             flush(batch)
         tm["pinned_alloc"] = assembler.alloc_seconds
+        decode_threads = {k_: round(v_, 3) for k_, v_ in assembler.worker_seconds.items()}
+        decode_threads["threads"] = len(assembler.threads)
         while in_flight:
             finish(in_flight.pop(0))
     seconds = time.perf_counter() - t_start
@@ -632,6 +635,7 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
     if all_failed:
         raise _lib.DssError(f"eigensolver did not converge for {len(all_failed)} image(s): {all_failed[:8]}")
     return {"images": len(todo), "seconds": seconds, "images_per_s": len(todo) / max(seconds, 1e-9),
+            "decode_thread_seconds_summed": decode_threads,
             "main_thread_seconds": {"waiting_for_decoders": tm["decode_wait"],
                                     "pinned_alloc_in_decoders": tm["pinned_alloc"], "kernel_launches": tm["launch"],
                                     "waiting_for_gpu": tm["wait_gpu"], "writer_submit": tm["submit"], "total": seconds}}

@@ -191,6 +191,9 @@ class BatchAssembler:
         self._live = 0
         self._stop = False
         self.alloc_seconds = 0.0
+        # summed over the decode threads (seconds): file decode, waiting for a free batch of the image's shape, colour
+        # swap into the page-locked row
+        self.worker_seconds = {"decode": 0.0, "wait_for_batch": 0.0, "convert": 0.0}
         self.threads: List[threading.Thread] = []
 
     # -- called with self._cv held
@@ -235,15 +238,22 @@ class BatchAssembler:
                 return b, row
 
     def _worker(self):
+        import time as _t
         import numpy as np
+        t_dec = t_wait = t_conv = 0.0
         try:
             while True:
                 with self._cv:
                     i = next(self._it, None) if not self._stop else None
                 if i is None:
                     break
+                t0 = _t.perf_counter()
                 pixels, is_bgr, path, index = self.load(i)
+                t1 = _t.perf_counter()
                 b, row = self._assign((int(pixels.shape[0]), int(pixels.shape[1])), path, index)
+                t2 = _t.perf_counter()
+                t_dec += t1 - t0
+                t_wait += t2 - t1
                 dst = b.np[row]
                 if is_bgr:
                     import cv2
@@ -252,6 +262,7 @@ class BatchAssembler:
                         np.copyto(dst, out)
                 else:
                     np.copyto(dst, pixels)
+                t_conv += _t.perf_counter() - t2
                 with self._cv:
                     b.filled += 1
                     if b.closed and b.filled == b.assigned:
@@ -260,6 +271,9 @@ class BatchAssembler:
             self._ready.put(e)
         finally:
             with self._cv:
+                self.worker_seconds["decode"] += t_dec
+                self.worker_seconds["wait_for_batch"] += t_wait
+                self.worker_seconds["convert"] += t_conv
                 self._live -= 1
                 if self._live == 0:     # input exhausted and every row written: hand over the partly filled batches
                     for b in list(self._open.values()):

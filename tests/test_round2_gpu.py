@@ -372,12 +372,17 @@ def test_extract_all_host_pipeline_throughput(cuda, tmp_path):
         import tempfile
         shm = Path(tempfile.mkdtemp(dir="/dev/shm"))
         try:
-            st2 = ex.extract_all(str(tmp_path / "list.txt"), str(root), "dino_vits16", None, str(shm / "eigs"), K=5,
-                                 batch_size=128, seed=0)
-            assert len(list((shm / "eigs").iterdir())) == n
-            a = torch.load(shm / "eigs" / "im00077.pth"); b = torch.load(tmp_path / "eigs" / "im00077.pth")
+            rates = []
+            for rep in range(3):
+                st2 = ex.extract_all(str(tmp_path / "list.txt"), str(root), "dino_vits16", None, str(shm / f"eigs{rep}"), K=5,
+                                     batch_size=128, seed=0)
+                assert len(list((shm / f"eigs{rep}").iterdir())) == n
+                rates.append(st2["images_per_s"])
+            a = torch.load(shm / "eigs0" / "im00077.pth"); b = torch.load(tmp_path / "eigs" / "im00077.pth")
             assert torch.equal(a["eigenvectors"], b["eigenvectors"])      # batch composition does not change a result
-            rate_shm = st2["images_per_s"]
+            rate_shm = sorted(rates)[1]                                   # median of three
+            print("extract_all on tmpfs, three runs:", [round(r) for r in rates], st2["main_thread_seconds"],
+                  st2["decode_thread_seconds_summed"])
         finally:
             shutil.rmtree(shm, ignore_errors=True)
     # decode-only floor with the same thread pool
@@ -406,7 +411,8 @@ def test_extract_all_host_pipeline_throughput(cuda, tmp_path):
             f"extract_all_images_per_s {rate:.1f}\nextract_all_eigs_on_tmpfs_images_per_s {-1.0 if rate_shm is None else rate_shm:.1f}\n"
             f"extract_all_incl_model_setup_images_per_s {rate_total:.1f}\ndecode_only_images_per_s {dec_rate:.1f}\n"
             f"kernels_e2e_images_per_s {e2e:.1f}\nkernels_over_cli {e2e / best:.3f}\n"
-            f"decode_threads {iop.default_workers()}\nimages {n}\nmain_thread_seconds {st['main_thread_seconds']}\n")
+            f"decode_threads {iop.default_workers()}\nimages {n}\nmain_thread_seconds {st['main_thread_seconds']}\n"
+            f"decode_thread_seconds_summed {st['decode_thread_seconds_summed']}\n")
     # VERDICT r1 item 7 asks for the CLI path within 2x of the kernels' end-to-end rate; the assertion keeps a margin for
     # box-to-box differences in host cores and file systems (measured: 1.4x on tmpfs, 2.6-3.3x on the overlay root)
     assert best >= 0.4 * min(dec_rate, e2e), (rate, rate_shm, dec_rate, e2e)

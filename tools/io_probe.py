@@ -39,7 +39,7 @@ def main():
         for k, v in old.items():
             if v is None: os.environ.pop(k, None)
             else: os.environ[k] = v
-        print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, flush=True)
+        print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, st.get("decode_thread_seconds_summed"), flush=True)
         shutil.rmtree(tmp / f"eigs{run}", ignore_errors=True)
 
     # what one .pth costs on this box's file systems (torch.save + rename, like the writers): serial and 4 processes
@@ -71,12 +71,14 @@ def main():
         global run
         run += 1
         st = ex.extract_all(str(keep / "list.txt"), str(root), "dino_vits16", None, str(shm / f"eigs{run}"), K=5, batch_size=128, seed=0, **kw)
-        print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, flush=True)
+        print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, st.get("decode_thread_seconds_summed"), flush=True)
         shutil.rmtree(shm / f"eigs{run}", ignore_errors=True)
 
-    for rep in range(3):
+    for rep in range(4):
         go("default")
         go_shm("out_on_devshm")
+        go_shm("out_on_devshm_16thr", num_workers=16)
+        go_shm("out_on_devshm_48thr", num_workers=48)
     if shm is not None:
         shutil.rmtree(shm, ignore_errors=True)
     for rep in range(0):
