@@ -30,6 +30,30 @@ PKG = "deep-spectral-segmentation_b200"
 METRIC = "images/sec (features+eigs, 480px dino_vits16 K=5)"
 
 
+
+def usable_cpus() -> int:
+    """CPUs this job may use: affinity mask and cgroup quota, not os.cpu_count() (the B200 hosts show 128 hardware
+    threads to a container whose CPU quota is 16; a pool sized for 128 is throttled by the scheduler)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,7 +215,7 @@ class CpuPool:
     def __init__(self, model_name, threads_per_worker=2, max_workers=64, need_vit=True):
         import multiprocessing as mp
         from concurrent.futures import ProcessPoolExecutor
-        self.cores = os.cpu_count() or 1
+        self.cores = usable_cpus()
         self.threads = threads_per_worker
         self.workers = max(1, min(self.cores // threads_per_worker, max_workers))
         # numpy/scipy's BLAS (OpenBLAS) sizes its thread pool from the environment at import time: without this every
@@ -275,7 +299,7 @@ def as_shipped_baseline(model_name, size, K, n_images, dev):
         paths.append(os.path.join(tmp, f"w{i}.npy"))
         np.save(paths[-1], W)                                                    # (hand-over to the worker pool: not timed)
     t_aff /= n_images
-    with CpuPool(model_name, threads_per_worker=1, max_workers=os.cpu_count() or 1, need_vit=False) as pool:
+    with CpuPool(model_name, threads_per_worker=1, max_workers=usable_cpus(), need_vit=False) as pool:
         pool.map(_affinity_eigs_task, [(paths[i % n_images], K) for i in range(pool.workers)])     # warm-up
         reps = max(1, (2 * pool.workers) // n_images)
         jobs = [(p_, K) for _ in range(reps) for p_ in paths]
@@ -301,7 +325,7 @@ def as_shipped_baseline(model_name, size, K, n_images, dev):
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     n = args.ref_images_per_step if args.ref_images_per_step > 0 else 2 * max(1, min(cores // 2, 64))
     value, dt, split = cpu_pool_images_per_sec(args.model, args.size, args.K, n, args.steps, args.warmup)
     sample = (f"{n} synthetic {args.size}x{args.size} images per step (a bounded sample of the step of the GPU arm); "
@@ -569,7 +593,7 @@ def run_c2(ctx: Ctx):
 
     # ---- CPU baselines + parity on a bounded sample (rank 0, N=1 only)
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cpus()
         n = min(args.parity_sample, B)
         feats = pipe._bufs["feats"][:n].cpu()          # features of the last step == images host_imgs[:n]
         evecs = out[1][:n].numpy().copy()
@@ -718,7 +742,7 @@ def run_c3(ctx: Ctx):
             "eigensolver": {"converged": int(info[:, 1].sum().item()), "of": B, "lanczos_steps_mean": steps_mean},
             "roofline": ctx.roofline(kernels), "kernels": kernels}
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cpus()
         n = min(8, B)
         tmp = tempfile.mkdtemp(prefix="dss_bench_")
         fh = feats[:n].cpu()
@@ -863,7 +887,7 @@ def run_c5(ctx: Ctx):
                "ms_per_step": ms / steps, "lanczos_steps_mean": m_steps, "converged": int(info[:, 1].sum().item()),
                "kernels": [k_ for k_ in kernels if k_["kernel"] in ("eigsh", "affinity", "attention", "gemm_fc1", "gemm_qkv")]}
         if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = usable_cpus()
             n = 2 if N >= 3600 else 4
             tmp = tempfile.mkdtemp(prefix="dss_bench_")
             fh = feats[:n].cpu()

@@ -626,6 +626,8 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
         tm["pinned_alloc"] = assembler.alloc_seconds
         decode_threads = {k_: round(v_, 3) for k_, v_ in assembler.worker_seconds.items()}
         decode_threads["threads"] = len(assembler.threads)
+        if assembler.trace is not None:
+            decode_threads["trace"] = [(round(t_ - t_start, 4), ev_, d_) for t_, ev_, d_ in sorted(assembler.trace)]
         while in_flight:
             finish(in_flight.pop(0))
     seconds = time.perf_counter() - t_start

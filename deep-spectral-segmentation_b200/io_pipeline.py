@@ -28,12 +28,39 @@ from typing import Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
 import torch
 
 
-def default_workers(cap: int = 32) -> int:
-    """Decode threads: DSS_IO_DECODE_THREADS, else min(cap, host threads - 1)."""
+def available_cpus() -> int:
+    """CPUs this process may actually use: the scheduler affinity mask and the cgroup CPU quota (cpu.max of cgroup v2,
+    cfs_quota_us of v1), not os.cpu_count(). On the B200 hosts a container sees 128 hardware threads and has a quota of
+    16: with 32 decode threads the whole process group was throttled for ~100 ms at a time (cpu.stat nr_throttled), which
+    stalled the thread that feeds the GPU as well."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            quota = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            period = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
+def default_workers(cap: int = 32, reserve: int = 4) -> int:
+    """Decode threads: DSS_IO_DECODE_THREADS, else the usable CPUs minus ``reserve`` (the thread that feeds the GPU and
+    the writer processes), at most ``cap``."""
     env = os.environ.get("DSS_IO_DECODE_THREADS")
     if env:
         return max(1, int(env))
-    return max(1, min(cap, (os.cpu_count() or 2) - 1))
+    cpus = available_cpus()
+    return max(1, min(cap, cpus - reserve if cpus > 2 * reserve else cpus - 1))
 
 
 class ImagePrefetcher:
@@ -194,6 +221,7 @@ class BatchAssembler:
         # summed over the decode threads (seconds): file decode, waiting for a free batch of the image's shape, colour
         # swap into the page-locked row
         self.worker_seconds = {"decode": 0.0, "wait_for_batch": 0.0, "convert": 0.0}
+        self.trace: Optional[list] = [] if os.environ.get("DSS_IO_TRACE") else None   # (seconds, event, detail)
         self.threads: List[threading.Thread] = []
 
     # -- called with self._cv held
@@ -201,6 +229,9 @@ class BatchAssembler:
         b.closed = True
         self._open.pop(b.key, None)
         self._pending -= b.assigned
+        if self.trace is not None:
+            import time as _t
+            self.trace.append((_t.perf_counter(), "closed", id(b)))
         if b.filled == b.assigned:
             self._ready.put(b)
 
@@ -223,10 +254,14 @@ class BatchAssembler:
                         ring["free"].append(len(ring["bufs"]) - 1)
                         self.alloc_seconds += _t.perf_counter() - t0
                     if not ring["free"]:
+                        if self.trace is not None:
+                            self.trace.append((_t.perf_counter(), "no_free_batch", len(ring["bufs"])))
                         self._cv.wait(0.5)
                         continue
                     slot = ring["free"].pop()
                     b = self._open[key] = HostBatch(key, slot, ring["bufs"][slot], ring["cap"])
+                    if self.trace is not None:
+                        self.trace.append((_t.perf_counter(), "opened", id(b)))
                 row = b.assigned
                 b.assigned += 1
                 b.items.append((path, index))
@@ -266,6 +301,8 @@ class BatchAssembler:
                 with self._cv:
                     b.filled += 1
                     if b.closed and b.filled == b.assigned:
+                        if self.trace is not None:
+                            self.trace.append((_t.perf_counter(), "ready", id(b)))
                         self._ready.put(b)
         except BaseException as e:  # noqa: BLE001  (re-raised by the consumer)
             self._ready.put(e)
@@ -286,8 +323,13 @@ class BatchAssembler:
         n = max(1, min(self.num_workers, total))
         self._live = n
         self.threads = [threading.Thread(target=self._worker, name=f"dss-decode-{t}", daemon=True) for t in range(n)]
+        import time as _t
+        if self.trace is not None:
+            self.trace.append((_t.perf_counter(), "starting_threads", n))
         for t in self.threads:
             t.start()
+        if self.trace is not None:
+            self.trace.append((_t.perf_counter(), "threads_started", n))
         got = 0
         try:
             while got < total:
@@ -295,6 +337,8 @@ class BatchAssembler:
                 if isinstance(b, BaseException):
                     raise b
                 got += b.assigned
+                if self.trace is not None:
+                    self.trace.append((_t.perf_counter(), "consumer_got", id(b)))
                 yield b
         finally:
             with self._cv:
@@ -307,6 +351,9 @@ class BatchAssembler:
         """The consumer is done with the batch's page-locked memory (its host->device copy has completed)."""
         with self._cv:
             self._rings[b.key]["free"].append(b.slot)
+            if self.trace is not None:
+                import time as _t
+                self.trace.append((_t.perf_counter(), "released", id(b)))
             self._cv.notify_all()
 
 

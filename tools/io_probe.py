@@ -74,7 +74,25 @@ def main():
         print("PROBE", label, round(st["images_per_s"]), {k: round(v, 3) for k, v in st["main_thread_seconds"].items()}, st.get("decode_thread_seconds_summed"), flush=True)
         shutil.rmtree(shm / f"eigs{run}", ignore_errors=True)
 
-    for rep in range(4):
+    os.environ["DSS_IO_TRACE"] = "1"
+    for rep in range(2):
+        run += 1
+        st = ex.extract_all(str(tmp / "list.txt"), str(root), "dino_vits16", None, str(shm / f"eigs{run}"), K=5, batch_size=128, seed=0)
+        tr = st["decode_thread_seconds_summed"].pop("trace")
+        ids = {}
+        print("PROBE trace run", rep, round(st["images_per_s"]), st["main_thread_seconds"], st["decode_thread_seconds_summed"], flush=True)
+        for t_, ev_, d_ in tr:
+            if ev_ in ("opened", "closed", "ready", "consumer_got", "released"):
+                d_ = ids.setdefault(d_, len(ids))
+            print("PROBE   ", f"{t_:8.4f}", ev_, d_, flush=True)
+        shutil.rmtree(shm / f"eigs{run}", ignore_errors=True)
+    os.environ.pop("DSS_IO_TRACE")
+    for rep in range(3):
+        go("default")
+        go_shm("out_on_devshm")
+        go_shm("out_on_devshm_8thr", num_workers=8)
+        go_shm("out_on_devshm_16thr", num_workers=16)
+    for rep in range(0):
         go("default")
         go_shm("out_on_devshm")
         go_shm("out_on_devshm_16thr", num_workers=16)
