@@ -63,6 +63,28 @@ def default_workers(cap: int = 32, reserve: int = 4) -> int:
     return max(1, min(cap, cpus - reserve if cpus > 2 * reserve else cpus - 1))
 
 
+_LIMITED = False
+
+
+def limit_library_threads() -> None:
+    """Called before this module starts its own decode threads: OpenCV's internal pool is switched off
+    (cv2.setNumThreads(1): every cvtColor / resize would otherwise fan out over a pool sized by os.cpu_count(), 128
+    spinning threads on a 16-CPU quota) and torch's intra-op pool is capped at the usable CPUs. The parallelism of the
+    host pipeline is the decode threads themselves."""
+    global _LIMITED
+    if _LIMITED:
+        return
+    _LIMITED = True
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except ImportError:
+        pass
+    cpus = available_cpus()
+    if torch.get_num_threads() > cpus:
+        torch.set_num_threads(cpus)
+
+
 class ImagePrefetcher:
     """Iterates ``load(i)`` for i in ``indices`` in order, keeping up to ``lookahead`` loads in flight on a thread pool."""
 
@@ -80,6 +102,7 @@ class ImagePrefetcher:
             for i in self.indices:
                 yield self.load(i)
             return
+        limit_library_threads()
         with ThreadPoolExecutor(self.num_workers, thread_name_prefix="dss-decode") as pool:
             pending: deque = deque()
             it = iter(self.indices)
@@ -320,6 +343,7 @@ class BatchAssembler:
         total = len(self.indices)
         if total == 0:
             return
+        limit_library_threads()
         n = max(1, min(self.num_workers, total))
         self._live = n
         self.threads = [threading.Thread(target=self._worker, name=f"dss-decode-{t}", daemon=True) for t in range(n)]

@@ -75,7 +75,7 @@ def main():
         shutil.rmtree(shm / f"eigs{run}", ignore_errors=True)
 
     os.environ["DSS_IO_TRACE"] = "1"
-    for rep in range(2):
+    for rep in range(1):
         run += 1
         st = ex.extract_all(str(tmp / "list.txt"), str(root), "dino_vits16", None, str(shm / f"eigs{run}"), K=5, batch_size=128, seed=0)
         tr = st["decode_thread_seconds_summed"].pop("trace")
