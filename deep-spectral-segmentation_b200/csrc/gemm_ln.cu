@@ -54,7 +54,29 @@ struct LnParams {
   int M, N;
 };
 
-template <bool GELU, int BN>
+// Work items of one cluster: full rounds over the row blocks with every n-tile, then ONE tail item in which the
+// remaining row blocks (fewer than clusters) are split by n-tile ranges over all clusters: with whole blocks only, 296
+// images (2084 row blocks) gave 6 of 74 clusters a 15th block while 68 idled for a block's worth of time (6.5 % of
+// the kernel).
+struct LnItem { int c, nt0, nt1; };
+__device__ __forceinline__ bool ln_item(int i, int cid, int ncl, int units, int tiles_n, LnItem& it) {
+  const int rounds = units / ncl, rem = units - rounds * ncl;
+  if (i < rounds) { it.c = cid + i * ncl; it.nt0 = 0; it.nt1 = tiles_n; return true; }
+  if (i > rounds || rem == 0) return false;
+  int seg = ncl / rem;                       // clusters available per remaining block
+  if (seg > tiles_n) seg = tiles_n;
+  if (seg < 1) seg = 1;
+  const int blk = cid / seg, part = cid - blk * seg;
+  if (blk >= rem) return false;
+  it.c = rounds * ncl + blk;
+  it.nt0 = (tiles_n * part) / seg;
+  it.nt1 = (tiles_n * (part + 1)) / seg;
+  return it.nt1 > it.nt0;
+}
+
+// CL = CTAs per cluster: 2 = the pair shares every weight tile by TMA multicast (each CTA loads half), 1 = every CTA
+// loads its own weight tiles (no coupling between CTAs).
+template <bool GELU, int BN, int CL>
 __global__ void __launch_bounds__(LG_THREADS, 1)
 gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int pairs,
                            LnParams p) {
@@ -80,8 +102,8 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       gbase + Cfg::A_BYTES + STAGES * B_STAGE + Cfg::STAGING + Cfg::VEC_BYTES + 8 * Cfg::NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)cluster_ctarank();
-  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
   const int tiles_n = p.N / BN;
 
   if (warp == 0 && lane == 0) {
@@ -89,7 +111,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
     tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(b_full(s), 1);
-      mbar_init(b_empty(s), 2);   // released by the MMA warps of both CTAs (each multicasts into the other's ring)
+      mbar_init(b_empty(s), CL);  // released by the MMA warps of both CTAs (each multicasts into the other's ring)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull(i), 1);
@@ -118,14 +140,20 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       const uint32_t uB = __shfl_sync(0xffffffffu, sB, 0);
       int s = 0;
       uint32_t ph = 0;
-      for (int c = cid; c < pairs; c += ncl) {
-        for (int nt = 0; nt < tiles_n; ++nt) {
+      LnItem it;
+      for (int i = 0; ln_item(i, cid, ncl, pairs, tiles_n, it); ++i) {
+        for (int nt = it.nt0; nt < it.nt1; ++nt) {
           for (int k = 0; k < LG_SLABS; ++k) {
             mbar_wait(b_empty(s), ph ^ 1u);
             if (elect_one()) {
               mbar_arrive_expect_tx(b_full(s), B_STAGE);
-              tma_load_2d_mc(uB + s * B_STAGE + rank * (B_STAGE / 2), &tmB, b_full(s), k * 64, nt * BN + rank * (BN / 2),
-                             (uint16_t)0x3);
+              if constexpr (CL == 2) {
+                tma_load_2d_mc(uB + s * B_STAGE + rank * (B_STAGE / 2), &tmB, b_full(s), k * 64, nt * BN + rank * (BN / 2),
+                               (uint16_t)0x3);
+              } else {
+                tma_load_2d(uB + s * B_STAGE, &tmB, b_full(s), k * 64, nt * BN);
+                tma_load_2d(uB + s * B_STAGE + B_STAGE / 2, &tmB, b_full(s), k * 64, nt * BN + BN / 2);
+              }
             }
             __syncwarp();
             if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -139,14 +167,15 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       const uint32_t utmem = __shfl_sync(0xffffffffu, tmem_base, 0);
       int s = 0, lt = 0, li = 0;
       uint32_t ph = 0;
-      for (int c = cid; c < pairs; c += ncl, ++li) {
-        for (int nt = 0; nt < tiles_n; ++nt, ++lt) {
+      LnItem it;
+      for (; ln_item(li, cid, ncl, pairs, tiles_n, it); ++li) {
+        for (int nt = it.nt0; nt < it.nt1; ++nt, ++lt) {
           const int buf = lt & 1;
           mbar_wait(tempty(buf), ((lt >> 1) & 1) ^ 1u);
           tc_fence_after();
           const uint32_t acc = utmem + buf * BN;
           for (int k = 0; k < LG_SLABS; ++k) {
-            if (nt == 0) mbar_wait(a_full(k), li & 1);   // slab k of this block's normalised panel is in place
+            if (nt == it.nt0) mbar_wait(a_full(k), li & 1);   // slab k of this block's normalised panel is in place
             mbar_wait(b_full(s), ph);
             tc_fence_after();
             const uint64_t adesc = umma_desc_sw128(uA + k * LG_SLAB_BYTES);
@@ -155,8 +184,9 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
                 umma_f16_ss(acc, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-              umma_commit_mc(b_empty(s), (uint16_t)0x3);
-              if (nt == tiles_n - 1) umma_commit(a_free(k));   // last reader of slab k: the next block may overwrite it
+              if constexpr (CL == 2) umma_commit_mc(b_empty(s), (uint16_t)0x3);
+              else umma_commit(b_empty(s));
+              if (nt == it.nt1 - 1) umma_commit(a_free(k));   // last reader of slab k: the next block may overwrite it
             }
             __syncwarp();
             if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -167,57 +197,81 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       }
     }
   } else if (warp < 4 + LG_EPI_WARPS) {
-    // ---- epilogue: all 16 warps cooperate on one 64-column output box at a time (gemm.cu's TMA-store path)
+    // ---- epilogue: two independent groups of 8 warps, each owning every other 64-column output box (own staging buffer,
+    // own named barrier). While one group waits for its TMEM load or sits in its barrier the other one computes: with
+    // all 16 warps in lock step on one box, 28 % of the epilogue's time was the exposed tcgen05.ld latency and 23 % the
+    // two 512-thread barriers per box (ncu source view), and the epilogue -- not the tensor core -- set the pace.
     const int ew = warp - 4;
-    const int q = warp & 3, sl = ew >> 2;
+    const int q = warp & 3, h = (ew >> 2) & 1, grp = ew >> 3;   // TMEM lane quadrant, 32-column half of the box, group
     const int row = q * 32 + lane;
-    constexpr int W = 16;   // columns per warp slice
-    const bool issuer = (ew == 0) && (lane == 0);
+    constexpr int W = 16;                                       // columns per tcgen05.ld
+    const bool issuer = ((ew & 7) == 0) && (lane == 0);
+    const uint32_t sbuf = sStage + grp * LG_BOX_BYTES;
+    const uint32_t srow = sbuf + row * 128;
     int lt = 0, cc = 0;
-    for (int c = cid; c < pairs; c += ncl) {
-      const int m0 = (2 * c + rank) * LG_BM;
-      for (int nt = 0; nt < tiles_n; ++nt, ++lt) {
+    LnItem it;
+    for (int i = 0; ln_item(i, cid, ncl, pairs, tiles_n, it); ++i) {
+      const int m0 = (CL * it.c + rank) * LG_BM;
+      for (int nt = it.nt0; nt < it.nt1; ++nt, ++lt) {
         const int buf = lt & 1;
         mbar_wait(tfull(buf), (lt >> 1) & 1);
         tc_fence_after();
+        // the last box of this tile that belongs to this group (-1: none): the accumulator is released after its load
+        int last_own = -1;
+#pragma unroll
+        for (int b = 0; b < NT_BOX; ++b)
+          if (((cc + b) & 1) == grp) last_own = b;
+        if (last_own < 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(buf));
+        }
 #pragma unroll 1
         for (int b = 0; b < NT_BOX; ++b, ++cc) {
+          if ((cc & 1) != grp) continue;
           const int nc = nt * BN + b * 64;
-          float bias_r[W];
-#pragma unroll
-          for (int j = 0; j < W; j += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + sl * W + j));
-            bias_r[j] = bv.x; bias_r[j + 1] = bv.y; bias_r[j + 2] = bv.z; bias_r[j + 3] = bv.w;
-          }
-          uint32_t r[W];
-          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + b * 64 + sl * W, r);
+          uint32_t r0[W], r1[W];
+          const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + b * 64 + h * 32;
+          tmem_ld_32x16(tcol, r0);
+          tmem_ld_32x16(tcol + W, r1);
           tmem_ld_wait();
-          if (b == NT_BOX - 1) {
+          if (b == last_own) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(buf));
           }
-          float xv[W];
+          uint32_t pk[W];   // 32 columns of this row as 16 packed half2
 #pragma unroll
-          for (int e = 0; e < W; e += 2) {
-            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])),
-                                   pack_f32x2(bias_r[e], bias_r[e + 1])), xv[e], xv[e + 1]);
-            if constexpr (GELU) gelu_erf_x2(xv[e], xv[e + 1], xv[e], xv[e + 1]);
+          for (int j = 0; j < 2; ++j) {
+            float bias_r[W];
+#pragma unroll
+            for (int e = 0; e < W; e += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + h * 32 + j * W + e));
+              bias_r[e] = bv.x; bias_r[e + 1] = bv.y; bias_r[e + 2] = bv.z; bias_r[e + 3] = bv.w;
+            }
+#pragma unroll
+            for (int e = 0; e < W; e += 2) {
+              const uint32_t a0 = j == 0 ? r0[e] : r1[e], a1 = j == 0 ? r0[e + 1] : r1[e + 1];
+              float x0, x1;
+              unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a0), __uint_as_float(a1)),
+                                     pack_f32x2(bias_r[e], bias_r[e + 1])), x0, x1);
+              if constexpr (GELU) gelu_erf_x2(x0, x1, x0, x1);
+              pk[j * (W / 2) + (e >> 1)] = pack_half2(x0, x1);
+            }
           }
-          if (issuer) tma_store_wait_read<1>();   // the store issued two boxes ago has finished reading this buffer
-          asm volatile("bar.sync 1, %0;" ::"n"(LG_EPI_WARPS * 32) : "memory");
-          const uint32_t sbuf = sStage + (cc & 1) * LG_BOX_BYTES;
-          const uint32_t srow = sbuf + row * 128;
+          if (issuer) tma_store_wait_read<0>();   // this group's previous store has finished reading the buffer
+          if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int j = sl * 2 + h;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ (row & 7)) << 4)),
-                         "r"(pack_half2(xv[h * 8 + 0], xv[h * 8 + 1])), "r"(pack_half2(xv[h * 8 + 2], xv[h * 8 + 3])),
-                         "r"(pack_half2(xv[h * 8 + 4], xv[h * 8 + 5])), "r"(pack_half2(xv[h * 8 + 6], xv[h * 8 + 7]))
+          for (int i = 0; i < 4; ++i) {
+            const int j = h * 4 + i;   // 16-byte chunk of the 128-byte row, XOR-swizzled with the row (SW128)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ (row & 7)) << 4)), "r"(pk[i * 4 + 0]),
+                         "r"(pk[i * 4 + 1]), "r"(pk[i * 4 + 2]), "r"(pk[i * 4 + 3])
                          : "memory");
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, %0;" ::"n"(LG_EPI_WARPS * 32) : "memory");
+          if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
           if (issuer) {
             if (m0 < p.M) tma_store_2d(&tmC, sbuf, nc, m0);   // rows >= M are clipped by the tensor map
             tma_store_commit();
@@ -315,12 +369,14 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         put_slab(k + 1, xb);
       }
     };
-    int li = 0;
-    for (int c = cid; c < pairs; c += ncl, ++li) {
-      const int m0 = (2 * c + rank) * LG_BM;
-      if (li == 0) stats(m0, 0);
-      write_panel(m0, li & 1, li);
-      if (c + ncl < pairs) stats((2 * (c + ncl) + rank) * LG_BM, (li + 1) & 1);   // next block: overlaps this block's MMAs
+    LnItem it, nx;
+    bool have = ln_item(0, cid, ncl, pairs, tiles_n, it);
+    if (have) stats((CL * it.c + rank) * LG_BM, 0);
+    for (int li = 0; have; ++li) {
+      write_panel((CL * it.c + rank) * LG_BM, li & 1, li);
+      have = ln_item(li + 1, cid, ncl, pairs, tiles_n, nx);
+      if (have) stats((CL * nx.c + rank) * LG_BM, (li + 1) & 1);   // next block: overlaps this block's MMAs
+      it = nx;
     }
   }
   tc_fence_before();
@@ -329,35 +385,41 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <bool GELU, int BN>
-static int launch_ln(const CUtensorMap& tmB, const CUtensorMap& tmC, const LnParams& p, cudaStream_t st, int kclass) {
+template <bool GELU, int BN, int CL>
+static int launch_ln_cl(const CUtensorMap& tmB, const CUtensorMap& tmC, const LnParams& p, cudaStream_t st, int kclass) {
   using Cfg = LnCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_f16_tcgen05_kernel<GELU, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DSS_CHECK_CUDA(cudaFuncSetAttribute(gemm_ln_f16_tcgen05_kernel<GELU, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM));
     attr_set = true;
   }
-  const int pairs = cdiv(cdiv(p.M, LG_BM), 2);
+  const int units = cdiv(cdiv(p.M, LG_BM), CL);   // row blocks (CL = 1) or pairs of row blocks (CL = 2)
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+  const int clusters = units < sms / CL ? units : sms / CL;
   LaunchScope scope(st, kclass);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * clusters);
+  cfg.gridDim = dim3(CL * clusters);
   cfg.blockDim = dim3(LG_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DSS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_f16_tcgen05_kernel<GELU, BN>, tmB, tmC, pairs, p));
+  DSS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_ln_f16_tcgen05_kernel<GELU, BN, CL>, tmB, tmC, units, p));
   DSS_CHECK_CUDA(cudaGetLastError());
   return DSS_OK;
+}
+
+template <bool GELU, int BN>
+static int launch_ln(const CUtensorMap& tmB, const CUtensorMap& tmC, const LnParams& p, cudaStream_t st, int kclass) {
+  static const int cl = [] { const char* e = getenv("DSS_LN_CLUSTER"); return e ? atoi(e) : 2; }();   // tuning (1 | 2)
+  return cl == 1 ? launch_ln_cl<GELU, BN, 1>(tmB, tmC, p, st, kclass) : launch_ln_cl<GELU, BN, 2>(tmB, tmC, p, st, kclass);
 }
 
 // tile width of the fused kernel for an N-column layer (0: not supported)
