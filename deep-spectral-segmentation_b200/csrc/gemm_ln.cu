@@ -30,13 +30,13 @@ constexpr int LG_EPI_WARPS = 16, LG_LN_WARPS = 8;
 constexpr int LG_THREADS = (4 + LG_EPI_WARPS + LG_LN_WARPS) * 32;
 constexpr int LG_BOX_BYTES = LG_BM * 128;
 
+// (Measured and dropped: storing the fp16 rows straight from registers with 256-bit st.global and spending the 32 KB of
+// staging on a fifth weight stage -- qkv 3.67 -> 4.68 ms, fc1 5.37 -> 5.50 ms per 296 images.)
 template <int BN> struct LnCfg {
   static constexpr int A_BYTES = LG_SLABS * LG_SLAB_BYTES;          // 96 KB
   static constexpr int B_STAGE = BN * 128;                          // BN rows x 64 f16
   static constexpr int STAGES = 4;
-  static constexpr int STAGING = 2 * LG_BOX_BYTES;                  // two 128 x 128 B output boxes (double buffered: with a
-                                                                    // single box every store serialised the 16 epilogue
-                                                                    // warps behind the TMA engine's read of the box)
+  static constexpr int STAGING = 2 * LG_BOX_BYTES;                  // one 128 x 128 B output box per epilogue group
   static constexpr int VEC_BYTES = 2 * 2 * LG_BM * 4;               // mean[2][128], rstd[2][128]
   static constexpr int NBARS = 2 * STAGES + 4 + 2 * LG_SLABS;
   static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + STAGING + VEC_BYTES + NBARS * 8 + 16;
@@ -197,89 +197,111 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       }
     }
   } else if (warp < 4 + LG_EPI_WARPS) {
-    // ---- epilogue: two independent groups of 8 warps, each owning every other 64-column output box (own staging buffer,
-    // own named barrier). While one group waits for its TMEM load or sits in its barrier the other one computes: with
-    // all 16 warps in lock step on one box, 28 % of the epilogue's time was the exposed tcgen05.ld latency and 23 % the
-    // two 512-thread barriers per box (ncu source view), and the epilogue -- not the tensor core -- set the pace.
-    const int ew = warp - 4;
-    const int q = warp & 3, h = (ew >> 2) & 1, grp = ew >> 3;   // TMEM lane quadrant, 32-column half of the box, group
-    const int row = q * 32 + lane;
-    constexpr int W = 16;                                       // columns per tcgen05.ld
-    const bool issuer = ((ew & 7) == 0) && (lane == 0);
-    const uint32_t sbuf = sStage + grp * LG_BOX_BYTES;
-    const uint32_t srow = sbuf + row * 128;
-    int lt = 0, cc = 0;
-    LnItem it;
-    for (int i = 0; ln_item(i, cid, ncl, pairs, tiles_n, it); ++i) {
-      const int m0 = (CL * it.c + rank) * LG_BM;
-      for (int nt = it.nt0; nt < it.nt1; ++nt, ++lt) {
-        const int buf = lt & 1;
-        mbar_wait(tfull(buf), (lt >> 1) & 1);
-        tc_fence_after();
-        // the last box of this tile that belongs to this group (-1: none): the accumulator is released after its load
-        int last_own = -1;
-#pragma unroll
-        for (int b = 0; b < NT_BOX; ++b)
-          if (((cc + b) & 1) == grp) last_own = b;
-        if (last_own < 0) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty(buf));
+    {
+      // ---- epilogue: two independent groups of 8 warps, each owning every other 64-column output box (own staging
+      // buffer, own named barrier): while one group sits in a barrier or waits for its TMA store the other computes.
+      // Inside a thread the box is a stream of four 8-column chunks, software pipelined: the tcgen05.ld and the bias
+      // loads of chunk j + 1 are issued before the arithmetic of chunk j, and those of the NEXT box's first chunk before
+      // this box's staging barriers (ncu: with load -> wait -> compute per box, 30 % of the epilogue's time was the
+      // exposed latency of those loads, and the epilogue, not the tensor core, set the pace).
+      static_assert(NT_BOX >= 2, "every tile needs a box for each of the two epilogue groups");
+      const int ew = warp - 4;
+      const int q = warp & 3, h = (ew >> 2) & 1, grp = ew >> 3;   // TMEM lane quadrant, 32-column half of the box, group
+      const int row = q * 32 + lane;
+      constexpr int W = 8, NCH = 32 / W;                          // columns per chunk, chunks per thread and box
+      const bool issuer = ((ew & 7) == 0) && (lane == 0);
+      const uint32_t sbuf = sStage + grp * LG_BOX_BYTES;
+      const uint32_t srow = sbuf + row * 128;
+      const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+      // this group's boxes in order: (item i, n-tile nt, box b); lt counts tiles. Box number lt NT_BOX + b over ALL boxes
+      // decides the owner: its parity is the group.
+      LnItem it;
+      int i = 0, nt = 0, b = -1, lt = -1;
+      bool valid = ln_item(0, cid, ncl, pairs, tiles_n, it);
+      if (valid) nt = it.nt0 - 1, b = NT_BOX - 1;
+      auto advance = [&]() {   // -> the next box that belongs to this group (valid = false at the end)
+        while (valid) {
+          if (++b == NT_BOX) {
+            b = 0;
+            ++lt;
+            if (++nt == it.nt1) {
+              valid = ln_item(++i, cid, ncl, pairs, tiles_n, it);
+              if (!valid) return;
+              nt = it.nt0;
+            }
+          }
+          if (((lt * NT_BOX + b) & 1) == grp) return;
         }
-#pragma unroll 1
-        for (int b = 0; b < NT_BOX; ++b, ++cc) {
-          if ((cc & 1) != grp) continue;
-          const int nc = nt * BN + b * 64;
-          uint32_t r0[W], r1[W];
-          const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + b * 64 + h * 32;
-          tmem_ld_32x16(tcol, r0);
-          tmem_ld_32x16(tcol + W, r1);
-          tmem_ld_wait();
-          if (b == last_own) {
+      };
+      uint32_t ra[W], rb[W];
+      float ba[W], bb[W];
+      auto issue = [&](int j, uint32_t (&r)[W], float (&bs)[W]) {   // loads of chunk j of the current box
+        tmem_ld_32x8(tlane + (lt & 1) * BN + b * 64 + h * 32 + j * W, r);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + nt * BN + b * 64 + h * 32 + j * W);
+        const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+        bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+      };
+      auto wait_tile = [&]() {   // first box of this group in the tile: wait until the tile's accumulator is complete
+        if (b == ((grp ^ (lt * NT_BOX)) & 1)) {
+          mbar_wait(tfull(lt & 1), (lt >> 1) & 1);
+          tc_fence_after();
+        }
+      };
+      advance();
+      if (valid) { wait_tile(); issue(0, ra, ba); }
+      while (valid) {
+        const int m0 = (CL * it.c + rank) * LG_BM, nc = nt * BN + b * 64, buf = lt & 1;
+        // is this the group's last box of the tile? (boxes b' > b of this tile with this group's parity)
+        bool last_own = true;
+#pragma unroll
+        for (int b2 = 1; b2 < NT_BOX; ++b2)
+          if (b + b2 < NT_BOX && ((b2 & 1) == 0)) last_own = false;
+        uint32_t pk[16];   // 32 columns of this row as 16 packed half2
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          tmem_ld_wait();   // chunk j has landed (the only tcgen05.ld in flight)
+          if (j + 1 < NCH) {
+            if (j & 1) issue(j + 1, ra, ba); else issue(j + 1, rb, bb);
+          } else if (last_own) {   // the accumulator is in registers: the MMA warp may reuse this TMEM buffer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(buf));
           }
-          uint32_t pk[W];   // 32 columns of this row as 16 packed half2
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            float bias_r[W];
-#pragma unroll
-            for (int e = 0; e < W; e += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nc + h * 32 + j * W + e));
-              bias_r[e] = bv.x; bias_r[e + 1] = bv.y; bias_r[e + 2] = bv.z; bias_r[e + 3] = bv.w;
-            }
-#pragma unroll
-            for (int e = 0; e < W; e += 2) {
-              const uint32_t a0 = j == 0 ? r0[e] : r1[e], a1 = j == 0 ? r0[e + 1] : r1[e + 1];
-              float x0, x1;
-              unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a0), __uint_as_float(a1)),
-                                     pack_f32x2(bias_r[e], bias_r[e + 1])), x0, x1);
-              if constexpr (GELU) gelu_erf_x2(x0, x1, x0, x1);
-              pk[j * (W / 2) + (e >> 1)] = pack_half2(x0, x1);
-            }
-          }
-          if (issuer) tma_store_wait_read<0>();   // this group's previous store has finished reading the buffer
-          if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-          else asm volatile("bar.sync 2, 256;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = h * 4 + i;   // 16-byte chunk of the 128-byte row, XOR-swizzled with the row (SW128)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ (row & 7)) << 4)), "r"(pk[i * 4 + 0]),
-                         "r"(pk[i * 4 + 1]), "r"(pk[i * 4 + 2]), "r"(pk[i * 4 + 3])
-                         : "memory");
-          }
-          fence_proxy_async_smem();
-          if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-          else asm volatile("bar.sync 2, 256;" ::: "memory");
-          if (issuer) {
-            if (m0 < p.M) tma_store_2d(&tmC, sbuf, nc, m0);   // rows >= M are clipped by the tensor map
-            tma_store_commit();
+          for (int e = 0; e < W; e += 2) {
+            const uint32_t a0 = (j & 1) ? rb[e] : ra[e], a1 = (j & 1) ? rb[e + 1] : ra[e + 1];
+            const float c0 = (j & 1) ? bb[e] : ba[e], c1 = (j & 1) ? bb[e + 1] : ba[e + 1];
+            float x0, x1;
+            unpack_f32x2(add_f32x2(pack_f32x2(__uint_as_float(a0), __uint_as_float(a1)), pack_f32x2(c0, c1)), x0, x1);
+            if constexpr (GELU) gelu_erf_x2(x0, x1, x0, x1);
+            pk[j * (W / 2) + (e >> 1)] = pack_half2(x0, x1);
           }
         }
+        // next box of this group: start its first chunk now, so that the loads overlap the staging of this box
+        const int st_m0 = m0, st_nc = nc;
+        advance();
+        if (valid) { wait_tile(); issue(0, ra, ba); }
+        if (issuer) tma_store_wait_read<0>();   // this group's previous store has finished reading the buffer
+        if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int j16 = h * 4 + i4;   // 16-byte chunk of the 128-byte row, XOR-swizzled with the row (SW128)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j16 ^ (row & 7)) << 4)), "r"(pk[i4 * 4 + 0]),
+                       "r"(pk[i4 * 4 + 1]), "r"(pk[i4 * 4 + 2]), "r"(pk[i4 * 4 + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (issuer) {
+          if (st_m0 < p.M) tma_store_2d(&tmC, sbuf, st_nc, st_m0);   // rows >= M are clipped by the tensor map
+          tma_store_commit();
+        }
       }
+      if (issuer) tma_store_wait_all<0>();
     }
-    if (issuer) tma_store_wait_all<0>();
   } else {
     // ---- LayerNorm producers: warp w owns rows [16 w, 16 w + 16) of the block. They get the registers the service
     // warps gave up: 4 rows x 3 float4 per lane in flight in the statistics pass (the first, HBM, read of x) -- with 2

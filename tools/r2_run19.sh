@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -q -m gpu -x --timeout 300 -k "fused_layernorm or vit or forward or features" > gpurun_out/pytest_ln_pipe.log 2>&1
+echo "pytest rc $?"; tail -1 gpurun_out/pytest_ln_pipe.log
+for i in 1 2; do
+timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_lnpipe$i.json 2> gpurun_out/bench_lnpipe$i.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_lnpipe$i.json").read().strip().splitlines()[-1])
+print("bench", round(d["value"]), round(d["e2e"]["value"]), [(k["kernel"], round(k["total_ms"]/d["steps"],2), k["frac"]) for k in d["kernels"][:6]])
+PY
+done
+DSS_VIT_FUSED_LN=0 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_unf.json 2>/dev/null
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_unf.json").read().strip().splitlines()[-1])
+print("bench unfused", round(d["value"]), round(d["e2e"]["value"]), [(k["kernel"], round(k["total_ms"]/d["steps"],2), k["frac"]) for k in d["kernels"][:7]])
+PY
