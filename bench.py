@@ -460,6 +460,10 @@ class Ctx:
             self.dist.destroy_process_group()
 
 
+def ln_fused(d):
+    return d == 384 and os.environ.get("DSS_VIT_FUSED_LN", "1") != "0"
+
+
 def vit_alg(P, d, depth_full, N, n_images):
     """Algorithmic FLOPs of the ViT classes for n_images images: last block pruned to LN1 + K."""
     T = N + 1
@@ -478,7 +482,9 @@ def vit_alg(P, d, depth_full, N, n_images):
         "gemm_fc2": ("auto", L * 2.0 * M * hid * d, L * M * (hid * 2.0 + d * 8.0)),
         "gemm_kproj": ("tensor", 2.0 * M * d * d),
         "attention": ("tensor", L * 4.0 * n_images * (d // 64) * T * T * 64),
-        "layernorm": ("hbm", (2 * L + 1) * M * d * (4 + 2)),
+        # stand-alone LayerNorm launches per step: 2 per block + the one before the K projection; with the LayerNorm
+        # fused into the qkv / fc1 GEMMs (ViT-S, csrc/gemm_ln.cu) only the last one remains
+        "layernorm": ("hbm", (1 if ln_fused(d) else 2 * L + 1) * M * d * (4 + 2)),
         "im2col": ("hbm", n_images * (N * P * P * 3 + N * 3 * P * P * 2)),
     }
 

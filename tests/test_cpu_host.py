@@ -242,3 +242,19 @@ def test_process_writer_splits_a_batch_into_row_ranges(tmp_path):
         j = int(name[1:])
         assert torch.equal(d["row"], torch.from_numpy(arrays["v"][j])) and int(d["n"]) == j
     assert sum(a["v"].shape[0] for a, _ in sent) <= 10
+
+
+def test_available_cpus_respects_affinity_and_quota(monkeypatch):
+    """io_pipeline.available_cpus (pool sizing): never more than the affinity mask, at least 1, and the decode-thread
+    default leaves room for the GPU-feeding thread and the writers."""
+    import os
+    iop = load_pkg("io_pipeline")
+    n = iop.available_cpus()
+    assert 1 <= n <= (os.cpu_count() or 1)
+    if hasattr(os, "sched_getaffinity"):
+        assert n <= len(os.sched_getaffinity(0))
+    monkeypatch.delenv("DSS_IO_DECODE_THREADS", raising=False)
+    w = iop.default_workers()
+    assert 1 <= w <= max(1, n - 1) and w <= 32
+    monkeypatch.setenv("DSS_IO_DECODE_THREADS", "5")
+    assert iop.default_workers() == 5
