@@ -280,7 +280,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
       for (int j = 0; j < nt; ++j, ++m) {
         // tile B starts every item half a key tile behind tile A (A signals from the middle of its first tile): left
         // alone, the two groups drift into lock step within ~10 items and both sit in their MUFU phase together
-        if (j == 0 && g == 1) asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (j == 0 && g == 1) { __syncwarp(); asm volatile("bar.sync 3, 256;" ::: "memory"); }
         mbar_wait(s_full(g), m & 1);
         tc_fence_after();
         [[maybe_unused]] const int tb = (warp - 4) * 1024 + (m < 120 ? m : 120) * 8;   // trace slot (ablation builds)
@@ -382,10 +382,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
                 chunk(c, msc, false);
                 // release tile B's first key tile when tile A is half way through its first exponentials: the two
                 // groups then stay about half a period apart (one in its MUFU phase, the other loading / reducing)
-                if (c == 1 && j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+                if (c == 1 && j == 0 && g == 0) { __syncwarp(); asm volatile("bar.arrive 3, 256;" ::: "memory"); }
               }
             }
-            if (kc <= 32 && j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // (short first tile)
+            if (kc <= 32 && j == 0 && g == 0) { __syncwarp(); asm volatile("bar.arrive 3, 256;" ::: "memory"); }   // (short first tile)
           } else {
             // ---- later key tiles: exponentials are taken relative to the reference maximum of the EARLIER tiles right
             // away (softmax is shift invariant; fp16 P and the fp32 sums have 2^8 of headroom) with the row maximum
@@ -436,7 +436,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         } else {
           // nothing to compute, but keep the protocol: P_g(m) may only be announced once P_g V(m-1) has been issued
           // (the MMA warp probes p_full by parity and must never be lapped by two phases)
-          if (j == 0 && g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // tile B's start signal (see above)
+          if (j == 0 && g == 0) { __syncwarp(); asm volatile("bar.arrive 3, 256;" ::: "memory"); }   // tile B's start signal (see above)
           if (m > 0) mbar_wait(o_full(g), (m - 1) & 1);
           tc_fence_before();
           __syncwarp();
@@ -459,6 +459,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         // normalised [128 x 64] fp16 tile -> swizzled staging tile -> one TMA store (rows >= T are clipped by the
         // 3D tensor map). The elected thread first makes sure the previous item's store has finished reading.
         if (q == 0 && lane == 0) tma_store_wait_read<0>();
+        __syncwarp();   // named barriers are warp-aligned: reconverge after lane-conditional code
         asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory");
         const uint32_t srow = sO + g * FA_TILE + r * 128;
 #pragma unroll
@@ -472,6 +473,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
                        : "memory");
         }
         fence_proxy_async_smem();
+        __syncwarp();   // named barriers are warp-aligned: reconverge after lane-conditional code
         asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory");
         if (q == 0 && lane == 0) {
           tma_store_3d(&tmO, sO + g * FA_TILE, h * FA_D, q0, bh / heads);
@@ -479,7 +481,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid
         }
       } else if (!dead) {
         // rows beyond T inside a live tile (never lane quarter 0): only the two staging-tile barriers of the group
+        __syncwarp();   // named barriers are warp-aligned: reconverge after lane-conditional code
         asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory");
+        __syncwarp();   // named barriers are warp-aligned: reconverge after lane-conditional code
         asm volatile("bar.sync %0, 128;" ::"r"(4 + g) : "memory");
       }
     }

@@ -497,6 +497,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           }
           // the staging box is free once the store issued two boxes ago has finished READING it
           if (issuer) tma_store_wait_read<1>();
+          __syncwarp();   // named barriers are warp-aligned: reconverge after lane-conditional code
           asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
           const uint32_t sbuf = stage_u32 + (cc & 1) * BOX_BYTES;
           const uint32_t srow = sbuf + row * 128;
@@ -516,6 +517,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
           }
           fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();   // named barriers are warp-aligned: reconverge after lane-conditional code
           asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
           if (issuer) {
             if (live) {
@@ -571,6 +573,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
         // group-local barrier (ids 1, 2). Double-buffered staging: one barrier per chunk is enough, because a
         // thread reaches the barrier of chunk c only after finishing phase 2 of the previous user of buffer c^1.
+        __syncwarp();   // named barriers are warp-aligned: reconverge after lane-conditional code
         asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
         // Phase 2: 8 lanes x 16 B cover the 128 B of one row of the chunk, 4 rows per warp instruction
         if (nc < N) {

@@ -283,8 +283,8 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
         advance();
         if (valid) { wait_tile(); issue(0, ra, ba); }
         if (issuer) tma_store_wait_read<0>();   // this group's previous store has finished reading the buffer
-        if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (grp == 0) { __syncwarp(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
+        else { __syncwarp(); asm volatile("bar.sync 2, 256;" ::: "memory"); }
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const int j16 = h * 4 + i4;   // 16-byte chunk of the 128-byte row, XOR-swizzled with the row (SW128)
@@ -293,8 +293,8 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
                        : "memory");
         }
         fence_proxy_async_smem();
-        if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-        else asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (grp == 0) { __syncwarp(); asm volatile("bar.sync 1, 256;" ::: "memory"); }
+        else { __syncwarp(); asm volatile("bar.sync 2, 256;" ::: "memory"); }
         if (issuer) {
           if (st_m0 < p.M) tma_store_2d(&tmC, sbuf, st_nc, st_m0);   // rows >= M are clipped by the tensor map
           tma_store_commit();
