@@ -24,9 +24,30 @@ from . import extract_utils as utils
 torch.set_grad_enabled(False)  # extract.py:838
 
 
+def _rank_world() -> Tuple[int, int]:
+    """(rank, world size) of a multi-process launch (torchrun or anything else that sets RANK / WORLD_SIZE); (0, 1)
+    otherwise. Images are the only parallel axis of the path: every command below gives rank r the items
+    r, r + R, r + 2R, ... of its sorted work list, on the GPU LOCAL_RANK; the ranks exchange nothing and write
+    disjoint files, so `torchrun --nproc-per-node 8 extract.py extract_all ...` is the multi-GPU form of the command."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1") or 1)
+    rank = int(os.environ.get("RANK", "0") or 0)
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"RANK={rank} outside WORLD_SIZE={world}")
+    return rank, world
+
+
+def _my_share(items: list) -> list:
+    rank, world = _rank_world()
+    return items if world == 1 else items[rank::world]
+
+
 def _device():
     if not torch.cuda.is_available():
         raise _lib.DssError("a CUDA device is required: the hot path has no CPU implementation")
+    import os
+    if _rank_world()[1] > 1 and os.environ.get("LOCAL_RANK") is not None:
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
     return torch.device("cuda", torch.cuda.current_device())
 
 
@@ -126,7 +147,7 @@ def extract_features(images_list: str, images_root: Optional[str], model_name: s
 
         batcher = _Batcher(batch_size, flush)
         todo = []
-        for i in range(len(dataset)):
+        for i in _my_share(list(range(len(dataset)))):
             output_file = Path(output_dir) / f"{Path(dataset.filenames[i]).stem}.pth"
             if output_file.is_file():
                 print(f"Skipping existing file {str(output_file)}")
@@ -295,7 +316,7 @@ def extract_eigs(images_root: str, features_dir: str, output_dir: str, which_mat
               f"({batch_size} per launch) instead of forked CPU workers")
     _check_supported(which_matrix, which_color_matrix, image_color_lambda)
     dev = _device()
-    inputs = list(enumerate(sorted(Path(features_dir).iterdir())))
+    inputs = _my_share(list(enumerate(sorted(Path(features_dir).iterdir()))))
     import time
     start = time.time()
     all_failed: List[str] = []
@@ -366,7 +387,7 @@ def extract_single_region_segmentations(features_dir: str, eigs_dir: str, output
         --output_dir "./data/VOC2012/single_region_segmentation/patches" \
     """
     utils.make_output_dir(output_dir, assume_yes=yes)
-    inputs = utils.get_paired_input_files(features_dir, eigs_dir)
+    inputs = _my_share(utils.get_paired_input_files(features_dir, eigs_dir))
     dev = _device()
     with _png_writer_pool(4) as pool:
         def flush(key, items):
@@ -402,7 +423,7 @@ def extract_multi_region_segmentations(features_dir: str, eigs_dir: str, output_
         --output_dir "./data/VOC2012/multi_region_segmentation/fixed" \
     """
     utils.make_output_dir(output_dir, assume_yes=yes)
-    inputs = utils.get_paired_input_files(features_dir, eigs_dir)
+    inputs = _my_share(utils.get_paired_input_files(features_dir, eigs_dir))
     dev = _device()
     seed = 0 if random_state is None else int(random_state)
     with _png_writer_pool(4) as pool:
@@ -600,7 +621,7 @@ def extract_all(images_list: str, images_root: Optional[str], model_name: str, f
                 finish(in_flight.pop(0))
 
         todo = []
-        for i in range(len(dataset)):
+        for i in _my_share(list(range(len(dataset)))):
             file = dataset.filenames[i]
             if (Path(eigs_dir) / f"{file[:-4]}.pth").is_file():
                 print(f"Skipping existing file {str(Path(eigs_dir) / (file[:-4] + '.pth'))}")

@@ -258,3 +258,22 @@ def test_available_cpus_respects_affinity_and_quota(monkeypatch):
     assert 1 <= w <= max(1, n - 1) and w <= 32
     monkeypatch.setenv("DSS_IO_DECODE_THREADS", "5")
     assert iop.default_workers() == 5
+
+
+def test_cli_commands_shard_their_work_list_by_rank(monkeypatch):
+    """extract._my_share: under torchrun (RANK / WORLD_SIZE) every command takes the strided share of its sorted work
+    list; the shares partition the list, a single process keeps everything, a rank outside the world is an error."""
+    ex = load_pkg("extract")
+    items = list(range(23))
+    monkeypatch.delenv("RANK", raising=False); monkeypatch.delenv("WORLD_SIZE", raising=False)
+    assert ex._my_share(items) == items and ex._rank_world() == (0, 1)
+    seen = []
+    for r in range(4):
+        monkeypatch.setenv("RANK", str(r)); monkeypatch.setenv("WORLD_SIZE", "4")
+        share = ex._my_share(items)
+        assert share == items[r::4]
+        seen += share
+    assert sorted(seen) == items
+    monkeypatch.setenv("RANK", "4")
+    with pytest.raises(ValueError):
+        ex._rank_world()
