@@ -277,3 +277,32 @@ def test_cli_commands_shard_their_work_list_by_rank(monkeypatch):
     monkeypatch.setenv("RANK", "4")
     with pytest.raises(ValueError):
         ex._rank_world()
+
+
+def test_batch_assembler_closes_partial_batches_under_memory_pressure(tmp_path):
+    """Many shapes, few images each (the VOC situation): with max_pending small the assembler has to hand over partly
+    filled batches early (largest first) instead of holding one open batch per shape; nothing may be lost or doubled."""
+    import cv2
+    iop = load_pkg("io_pipeline"); utils = load_pkg("extract_utils")
+    rng = np.random.default_rng(1)
+    names = []
+    for i in range(120):
+        H, W = 16 + 8 * (i % 7), 24 + 8 * ((i // 7) % 5)       # 35 distinct shapes
+        name = f"v{i:04d}.png"
+        cv2.imwrite(str(tmp_path / name), rng.integers(0, 256, (H, W, 3), dtype=np.uint8))
+        names.append(name)
+    ds = utils.ImagesDataset(names, str(tmp_path))
+    asm = iop.BatchAssembler(ds.load_raw, range(len(ds)), capacity=64, num_workers=4, slots=2, max_pending=8,
+                             full_size_shapes=3, small_capacity=4)
+    seen, sizes = set(), []
+    for b in asm:
+        assert b.assigned <= b.capacity and b.filled == b.assigned
+        for row, (path, index) in enumerate(b.items):
+            assert index not in seen
+            seen.add(index)
+            want = ds[index][0]
+            assert tuple(want.shape[:2]) == b.key and torch.equal(b.host[row], want)
+        sizes.append(b.assigned)
+        asm.release(b)
+    assert seen == set(range(len(ds)))
+    assert max(sizes) < 64          # pressure closed the batches long before they were full
