@@ -35,10 +35,11 @@ constexpr int LG_BOX_BYTES = LG_BM * 128;
 template <int BN> struct LnCfg {
   static constexpr int A_BYTES = LG_SLABS * LG_SLAB_BYTES;          // 96 KB
   static constexpr int B_STAGE = BN * 128;                          // BN rows x 64 f16
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = BN == 128 ? 6 : 4;                  // 96 KB of weight tiles in flight either way
+  static constexpr int NACC = 512 / BN;                             // TMEM accumulator stages: 2 x 192 or 4 x 128 columns
   static constexpr int STAGING = 2 * LG_BOX_BYTES;                  // one 128 x 128 B output box per epilogue group
   static constexpr int VEC_BYTES = 2 * 2 * LG_BM * 4;               // mean[2][128], rstd[2][128]
-  static constexpr int NBARS = 2 * STAGES + 4 + 2 * LG_SLABS;
+  static constexpr int NBARS = 2 * STAGES + 2 * NACC + 2 * LG_SLABS;
   static constexpr int SMEM = A_BYTES + STAGES * B_STAGE + STAGING + VEC_BYTES + NBARS * 8 + 16;
   static constexpr int TMEM_COLS = 512;
   static_assert(SMEM <= 232448, "shared memory budget");
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1)
 gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int pairs,
                            LnParams p) {
   using Cfg = LnCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES, B_STAGE = Cfg::B_STAGE;
+  constexpr int STAGES = Cfg::STAGES, B_STAGE = Cfg::B_STAGE, NACC = Cfg::NACC;
   constexpr int NT_BOX = BN / 64;   // 64-column output boxes per tile
   extern __shared__ __align__(1024) uint8_t lg_smem_raw[];
   const uint32_t base = smem_u32(lg_smem_raw);
@@ -94,9 +95,9 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
   auto b_full = [&](int s) { return bar_base + 8u * s; };
   auto b_empty = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull = [&](int i) { return bar_base + 8u * (2 * STAGES + i); };
-  auto tempty = [&](int i) { return bar_base + 8u * (2 * STAGES + 2 + i); };
-  auto a_full = [&](int k) { return bar_base + 8u * (2 * STAGES + 4 + k); };
-  auto a_free = [&](int k) { return bar_base + 8u * (2 * STAGES + 4 + LG_SLABS + k); };
+  auto tempty = [&](int i) { return bar_base + 8u * (2 * STAGES + NACC + i); };
+  auto a_full = [&](int k) { return bar_base + 8u * (2 * STAGES + 2 * NACC + k); };
+  auto a_free = [&](int k) { return bar_base + 8u * (2 * STAGES + 2 * NACC + LG_SLABS + k); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * Cfg::NBARS;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(
       gbase + Cfg::A_BYTES + STAGES * B_STAGE + Cfg::STAGING + Cfg::VEC_BYTES + 8 * Cfg::NBARS);
@@ -113,7 +114,7 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), CL);  // released by the MMA warps of both CTAs (each multicasts into the other's ring)
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       mbar_init(tfull(i), 1);
       mbar_init(tempty(i), LG_EPI_WARPS);
     }
@@ -170,8 +171,8 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       LnItem it;
       for (; ln_item(li, cid, ncl, pairs, tiles_n, it); ++li) {
         for (int nt = it.nt0; nt < it.nt1; ++nt, ++lt) {
-          const int buf = lt & 1;
-          mbar_wait(tempty(buf), ((lt >> 1) & 1) ^ 1u);
+          const int buf = lt % NACC;
+          mbar_wait(tempty(buf), ((lt / NACC) & 1) ^ 1u);
           tc_fence_after();
           const uint32_t acc = utmem + buf * BN;
           for (int k = 0; k < LG_SLABS; ++k) {
@@ -237,21 +238,21 @@ gemm_ln_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid
       uint32_t ra[W], rb[W];
       float ba[W], bb[W];
       auto issue = [&](int j, uint32_t (&r)[W], float (&bs)[W]) {   // loads of chunk j of the current box
-        tmem_ld_32x8(tlane + (lt & 1) * BN + b * 64 + h * 32 + j * W, r);
+        tmem_ld_32x8(tlane + (lt % NACC) * BN + b * 64 + h * 32 + j * W, r);
         const float4* bp = reinterpret_cast<const float4*>(p.bias + nt * BN + b * 64 + h * 32 + j * W);
         const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
         bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
       };
       auto wait_tile = [&]() {   // first box of this group in the tile: wait until the tile's accumulator is complete
         if (b == ((grp ^ (lt * NT_BOX)) & 1)) {
-          mbar_wait(tfull(lt & 1), (lt >> 1) & 1);
+          mbar_wait(tfull(lt % NACC), (lt / NACC) & 1);
           tc_fence_after();
         }
       };
       advance();
       if (valid) { wait_tile(); issue(0, ra, ba); }
       while (valid) {
-        const int m0 = (CL * it.c + rank) * LG_BM, nc = nt * BN + b * 64, buf = lt & 1;
+        const int m0 = (CL * it.c + rank) * LG_BM, nc = nt * BN + b * 64, buf = lt % NACC;
         // is this the group's last box of the tile? (boxes b' > b of this tile with this group's parity)
         bool last_own = true;
 #pragma unroll
@@ -445,7 +446,11 @@ static int launch_ln(const CUtensorMap& tmB, const CUtensorMap& tmC, const LnPar
 }
 
 // tile width of the fused kernel for an N-column layer (0: not supported)
-int gemm_ln_tile_n(int N) { return N % 192 == 0 ? 192 : (N % 128 == 0 ? 128 : 0); }
+int gemm_ln_tile_n(int N) {
+  static const int prefer = [] { const char* e = getenv("DSS_LN_BN"); return e ? atoi(e) : 192; }();   // tuning (128 | 192)
+  if (prefer == 128 && N % 128 == 0) return 128;
+  return N % 192 == 0 ? 192 : (N % 128 == 0 ? 128 : 0);
+}
 
 // tmB: weights [N, 384] f16 with box rows gemm_ln_tile_n(N) / 2; tmC: output [M, N] f16 (make_tmap_out)
 int gemm_ln_f16_tc(const CUtensorMap& tmB, const CUtensorMap& tmC, const float* x, const float* gamma, const float* beta,
