@@ -936,6 +936,12 @@ def run_c5(ctx: Ctx):
 
 def main():
     args = parse()
+    try:   # this process's own CPU work (fp64 checks of the parity block, pinned-buffer fills): not 128 threads on 16 CPUs
+        import torch
+        if torch.get_num_threads() > usable_cpus():
+            torch.set_num_threads(usable_cpus())
+    except Exception:  # noqa: BLE001
+        pass
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -11,6 +11,15 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the CPU oracles (fp64 eigh, fp32 ViT) run on torch's intra-op pool: size it by the CPUs this container may use
+    # (the B200 hosts show 128 hardware threads behind a 16-CPU quota; 128 spinning threads get the process throttled)
+    try:
+        import torch
+        n = importlib.import_module("deep-spectral-segmentation_b200.io_pipeline").available_cpus()
+        if torch.get_num_threads() > n:
+            torch.set_num_threads(n)
+    except Exception:  # noqa: BLE001  (never let a sizing hint break test collection)
+        pass
 
 
 @pytest.fixture(scope="session")
